@@ -1,0 +1,43 @@
+"""Parity tolerances (the reference states none).
+
+All floating point: complex64 data, float64 scalars.  The reference's own fp32 error floor
+(complex64 vs complex128 inputs) is 1.2e-7 .. 2.9e-7 on the grid and <= 4e-6 on the scalars, and
+its baseline / tensorized variants differ from each other by up to 3.3e-7.
+"""
+import numpy as np
+
+GRID_MAX_REL = 1e-5      # max|d| / max|ref| over the whole grid (gate)
+GRID_MAX_REL_TIGHT = 2e-6  # stretch target; oracle-vs-reference is held to this
+GRID_NMSE = 1e-12        # sum|d|^2 / sum|ref|^2
+SCALAR_REL = 1e-5        # RSRP, EPRE
+NOISE_ABS_OF_EPRE = 1e-6  # noise is ~1e-14 when the estimate reproduces the pilots: absolute bound
+CFO_REL, CFO_ABS_OF_SCS = 1e-4, 1e-7
+TA_TIE_MARGIN = 1e-5     # TA must match exactly unless the two largest profile bins are this close
+
+
+def grid_errors(got, ref):
+    got = np.asarray(got)
+    ref = np.asarray(ref)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    d = np.abs(got.astype(np.complex128) - ref.astype(np.complex128))
+    peak = float(np.abs(ref).max())
+    mx = float(d.max()) / peak if peak > 0 else float(d.max())
+    den = float((np.abs(ref.astype(np.complex128)) ** 2).sum())
+    nmse = float((d ** 2).sum()) / den if den > 0 else float((d ** 2).sum())
+    return mx, nmse
+
+
+def check_scalars(got, ref, scs, ta_margin=None, tag=""):
+    """got/ref: (noise, rsrp, epre, ta, cfo_hz or None/nan)."""
+    g = [np.nan if v is None else float(v) for v in got]
+    r = [np.nan if v is None else float(v) for v in ref]
+    epre = abs(r[2])
+    assert abs(g[0] - r[0]) <= NOISE_ABS_OF_EPRE * epre + 1e-5 * abs(r[0]), (tag, "noise", g[0], r[0])
+    assert abs(g[1] - r[1]) <= SCALAR_REL * abs(r[1]), (tag, "rsrp", g[1], r[1])
+    assert abs(g[2] - r[2]) <= SCALAR_REL * abs(r[2]), (tag, "epre", g[2], r[2])
+    if g[3] != r[3]:
+        near_tie = ta_margin is not None and min(ta_margin) < TA_TIE_MARGIN
+        assert near_tie or abs(g[3] - r[3]) <= 1e-15, (tag, "time alignment", g[3], r[3], ta_margin)
+    assert np.isnan(g[4]) == np.isnan(r[4]), (tag, "cfo emptiness", g[4], r[4])
+    if not np.isnan(r[4]):
+        assert abs(g[4] - r[4]) <= CFO_REL * abs(r[4]) + CFO_ABS_OF_SCS * scs, (tag, "cfo", g[4], r[4])
