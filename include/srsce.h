@@ -1,0 +1,136 @@
+/* srsce.h -- C ABI of the B200-native srsRAN port channel estimator.
+ *
+ * This is the drop-in boundary for the ONE hot path of pjookim/srsran-ce-pytorch:
+ *
+ *   srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config)
+ *       reference: src/ce_rule_tensorized.py:745-937  (same in ce_rule_baseline.py:761, ce_dl_cnn.py:802)
+ *
+ * The reference has no FFI of its own (it is pure Python on torch eager ops); these entry points
+ * are what a ctypes binding of that function binds (see INTEGRATION.md for the stub).  Plain
+ * pointers and sizes only, no torch types, no C++ exceptions across the boundary.
+ *
+ * Ownership / threading contract
+ *   - The caller owns every device buffer passed to srsce_estimate / srsce_cnn_fill and keeps it
+ *     alive until the stream reaches the kernel.  The library allocates nothing per call, never
+ *     synchronises and never touches the default stream unless it is the stream passed in.
+ *   - A plan owns its (small) host tables and their device copies; it is immutable after creation
+ *     and may be shared by threads and streams.  A plan is bound to the CUDA device that was
+ *     current in srsce_plan_create.  Without a CUDA device, plan creation still succeeds
+ *     (host tables only, used by the CPU-side tests); compute calls on it fail with
+ *     SRSCE_ERR_NO_DEVICE.  There is no CPU compute path.
+ *   - Every function returns 0 on success or a negative SRSCE_ERR_* code; the message is in
+ *     srsce_last_error() (thread local).
+ */
+#ifndef SRSCE_H_
+#define SRSCE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSCE_ABI_VERSION 1
+
+#define SRSCE_MAX_LAYERS 4
+#define SRSCE_MAX_SYMBOLS 14   /* the reference's CFO tables assume a 14-symbol slot (:809-820) */
+#define SRSCE_MAX_TAPS 31      /* get_rc_filter(1, 3): longest raised-cosine filter (:184-234) */
+#define SRSCE_TA_FFT 4096      /* ce_rule_tensorized.py:677 */
+#define SRSCE_TA_WINDOW 144    /* floor((144/2)*4096/2048), :682 */
+
+enum {
+  SRSCE_OK = 0,
+  SRSCE_ERR_INVALID = -1,     /* ValueError in the reference (unknown smoothing :668, CP vector < 14 :815, ...) */
+  SRSCE_ERR_ASSERT = -2,      /* AssertionError in the reference (hop overlap :862, differing RE masks :869) */
+  SRSCE_ERR_UNSUPPORTED = -3, /* geometry outside what one CTA can hold */
+  SRSCE_ERR_NO_DEVICE = -4,
+  SRSCE_ERR_CUDA = -5
+};
+
+enum { SRSCE_SMOOTH_NONE = 0, SRSCE_SMOOTH_MEAN = 1, SRSCE_SMOOTH_FILTER = 2 };  /* :633-668 */
+enum { SRSCE_FILL_LINEAR = 0, SRSCE_FILL_CNN = 1 };  /* fill_ch_est_cdm of ce_rule_* (:237-354) / ce_dl_cnn.py:233-322 */
+
+/* One frequency hop: mirrors HopConfig (src/ce_rule_tensorized.py:13-21). */
+typedef struct srsce_hop_desc {
+  uint32_t dmrs_symbol_mask;  /* bit t set <=> DMRSsymbols[t]; 0 => the hop is absent */
+  int32_t prb_start;          /* PRBstart (0-based) */
+  int32_t n_prbs;             /* nPRBs; maskPRBs must be exactly [prb_start, prb_start+n_prbs) */
+  int32_t start_symbol;       /* startSymbol */
+  int32_t n_alloc_symbols;    /* nAllocatedSymbols */
+} srsce_hop_desc;
+
+/* Everything data independent about a call: HopConfig x2 + EstimatorConfig (:24-29) + tensor shapes. */
+typedef struct srsce_plan_desc {
+  int32_t n_prb_grid;         /* len(maskPRBs); n_sc = 12 * n_prb_grid <= 4096 */
+  int32_t n_sym;              /* received_rg.shape[1] (<= 14) */
+  int32_t n_layers;           /* pilots.shape[2], 1..4 */
+  int32_t n_cp;               /* entries of cp_ms that are valid (reference needs >= 14 with CFO compensation) */
+  uint16_t re_mask[2];        /* DMRSREmask[:, g] as 12 bits (bit k <=> row k), g < ceil(n_layers/2) */
+  int32_t smoothing;          /* SRSCE_SMOOTH_* */
+  int32_t cfo_compensate;     /* EstimatorConfig.CFOCompensate */
+  int32_t fill;               /* SRSCE_FILL_* */
+  double cnn_alpha;           /* CNNSmoothingAlpha (ce_dl_cnn.py:864-867); used only with SRSCE_FILL_CNN */
+  double scs_hz;              /* EstimatorConfig.scs */
+  double cp_ms[SRSCE_MAX_SYMBOLS]; /* EstimatorConfig.CyclicPrefixDurations (ms) */
+  srsce_hop_desc hop[2];      /* hop[1].dmrs_symbol_mask == 0 <=> single hop */
+} srsce_plan_desc;
+
+typedef struct srsce_plan srsce_plan;
+
+/* Shapes derived from a plan (what the caller must allocate). */
+typedef struct srsce_plan_info {
+  int32_t n_sc;               /* 12 * n_prb_grid */
+  int32_t n_sym;
+  int32_t n_layers;
+  int32_t n_cdm;              /* ceil(n_layers / 2) */
+  int32_t n_re;               /* pilots.shape[0] = n_prbs * REs per PRB */
+  int32_t n_dmrs_total;       /* pilots.shape[1] = pilot symbols of hop 1 + hop 2 */
+  int32_t n_taps;             /* raised-cosine taps (0 unless smoothing == filter) */
+  int32_t n_virtual;          /* virtual pilots per edge */
+  int32_t fft_size;           /* TA transform actually run (4096 / comb stride, or 4096 zero-stuffed) */
+  int32_t cfo_defined;        /* 1 if some hop has >= 2 pilot symbols (cfo output is a scalar, not empty) */
+  int32_t smem_bytes;         /* dynamic shared memory of the fused kernel */
+  int32_t threads;            /* CTA size */
+  int32_t fill_terms;         /* operator terms per subcarrier (2 = lerp; CNN operator width otherwise) */
+  int32_t has_device;         /* device tables were uploaded */
+  int64_t bytes_per_unit;     /* algorithmic HBM bytes of one unit with pilots read once per unit */
+} srsce_plan_info;
+
+int srsce_abi_version(void);
+const char* srsce_last_error(void);
+
+int srsce_plan_create(const srsce_plan_desc* desc, srsce_plan** out);
+void srsce_plan_destroy(srsce_plan* plan);
+int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info);
+
+/* Host-side tables (for tests of the host logic; no device needed).
+ *   taps:      n_taps doubles                       get_rc_filter (:184-234)
+ *   fill_idx:  n_hop_sc * n_cdm int32               first pilot index of each band subcarrier's operator row
+ *   fill_coef: n_hop_sc * n_cdm * fill_terms float  operator coefficients (lerp: {1-a, a} encoded as {a})
+ * Pass NULL to skip a table. */
+int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, float* fill_coef);
+
+/* The fused per-slot path, batched over independent units (one unit = one reference call =
+ * one (slot, UE, rx antenna)):
+ *   rx_grid   complex64, unit u at rx_grid + u*rx_strides[0], element (sc, sym) at
+ *             + sc*rx_strides[1] + sym*rx_strides[2]   (strides in complex64 elements; the
+ *             reference layout [n_sc, n_sym] is {n_sc*n_sym, n_sym, 1})
+ *   pilots    complex64 [n_units / pilot_share][n_re][n_dmrs_total][n_layers] contiguous; unit u
+ *             reads block u / pilot_share (the rx antennas of one UE share its pilots)
+ *   beta      beta_dmrs
+ *   ch_est    complex64 [n_units][n_sc][n_sym][n_layers] contiguous, fully overwritten
+ *   scalars   double [n_units][6]: noise_est, rsrp, epre, time_alignment (s), cfo_hz, cfo_valid
+ *             (cfo_valid == 0 <=> the reference returns an empty cfo tensor)
+ *   stream    cudaStream_t
+ */
+int srsce_estimate(const srsce_plan* plan, const void* rx_grid, const int64_t rx_strides[3],
+                   const void* pilots, int32_t pilot_share, double beta, void* ch_est,
+                   double* scalars, int64_t n_units, void* stream);
+
+/* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
+int srsce_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRSCE_H_ */

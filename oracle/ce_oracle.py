@@ -430,7 +430,8 @@ def estimate(received_rg, pilots, beta_dmrs, hop1, hop2, config, fill: str = "te
     n_pil = h1.n_prbs * int(h1.re_mask[:, 0].sum()) * int(all_sym.sum())
     rsrp = acc.rsrp / float(n_pil) / float(n_layers)
     epre = acc.epre / float(n_pil)
-    noise = acc.noise / float(((n_layers + 1) // 2) * n_pil - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):      # one pilot in total: x/0 like the reference's tensors
+        noise = float(np.float64(acc.noise) / np.float64(((n_layers + 1) // 2) * n_pil - 1))
     ta = acc.ta / 2.0 if h2.present else acc.ta
     if cfg.cfo_compensate and acc.cfo is not None:
         rot = np.exp(1j * (2.0 * math.pi * t_sym * acc.cfo)).astype(c64)

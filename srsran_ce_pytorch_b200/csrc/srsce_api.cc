@@ -1,0 +1,112 @@
+// C ABI glue (include/srsce.h): argument checks, error strings, plan lifetime.  No C++ exception
+// leaves this file.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "srsce_internal.h"
+
+struct srsce_plan {
+  srsce::Plan impl;
+};
+
+namespace {
+thread_local std::string g_error;
+thread_local int g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+}  // namespace
+
+extern "C" {
+
+int srsce_abi_version(void) { return SRSCE_ABI_VERSION; }
+
+const char* srsce_last_error(void) { return g_error.c_str(); }
+
+int srsce_plan_create(const srsce_plan_desc* desc, srsce_plan** out) {
+  if (!desc || !out) return fail(SRSCE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  try {
+    srsce_plan* p = new srsce_plan();
+    std::string err;
+    int rc = srsce::build_plan(*desc, p->impl, err);
+    if (rc == SRSCE_OK) rc = srsce::upload_plan(p->impl, err);
+    if (rc != SRSCE_OK) {
+      srsce::release_plan(p->impl);
+      delete p;
+      return fail(rc, err);
+    }
+    *out = p;
+    return SRSCE_OK;
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
+void srsce_plan_destroy(srsce_plan* plan) {
+  if (!plan) return;
+  srsce::release_plan(plan->impl);
+  delete plan;
+}
+
+int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info) {
+  if (!plan || !info) return fail(SRSCE_ERR_INVALID, "null argument");
+  const srsce::PlanDev& v = plan->impl.dev;
+  memset(info, 0, sizeof *info);
+  info->n_sc = v.n_sc;
+  info->n_sym = v.n_sym;
+  info->n_layers = v.n_layers;
+  info->n_cdm = v.n_cdm;
+  info->n_re = v.n_re;
+  info->n_dmrs_total = v.n_dmrs_total;
+  info->n_taps = v.n_taps;
+  info->n_virtual = v.n_virtual;
+  info->fft_size = v.fft_size;
+  info->cfo_defined = v.cfo_defined;
+  info->smem_bytes = v.smem_bytes;
+  info->threads = srsce::kThreads;
+  info->fill_terms = plan->impl.fill_terms_host;
+  info->has_device = plan->impl.device >= 0;
+  info->bytes_per_unit = plan->impl.bytes_per_unit;
+  return SRSCE_OK;
+}
+
+int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, float* fill_coef) {
+  if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
+  const srsce::Plan& p = plan->impl;
+  if (taps) memcpy(taps, p.taps.data(), p.taps.size() * sizeof(double));
+  if (fill_idx) memcpy(fill_idx, p.fill_idx.data(), p.fill_idx.size() * sizeof(int32_t));
+  if (fill_coef) memcpy(fill_coef, p.fill_coef.data(), p.fill_coef.size() * sizeof(float));
+  return SRSCE_OK;
+}
+
+int srsce_estimate(const srsce_plan* plan, const void* rx_grid, const int64_t rx_strides[3], const void* pilots,
+                   int32_t pilot_share, double beta, void* ch_est, double* scalars, int64_t n_units, void* stream) {
+  g_launches = 0;
+  if (!plan || !rx_strides) return fail(SRSCE_ERR_INVALID, "null argument");
+  if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
+  if (n_units > 0 && (!rx_grid || !pilots || !ch_est || !scalars)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if (pilot_share < 1 || (n_units % pilot_share) != 0)
+    return fail(SRSCE_ERR_INVALID, "n_units must be a multiple of pilot_share (>= 1)");
+  if (!(beta != 0.0)) return fail(SRSCE_ERR_INVALID, "beta_dmrs must be non-zero");
+  if ((reinterpret_cast<uintptr_t>(ch_est) & 15u) || (reinterpret_cast<uintptr_t>(rx_grid) & 7u) ||
+      (reinterpret_cast<uintptr_t>(pilots) & 7u) || (reinterpret_cast<uintptr_t>(scalars) & 7u))
+    return fail(SRSCE_ERR_INVALID, "buffers must be aligned (ch_est 16 B, others 8 B)");
+  try {
+    std::string err;
+    const int rc = srsce::launch_estimate(plan->impl, rx_grid, rx_strides, pilots, pilot_share, beta, ch_est, scalars,
+                                          n_units, stream, &g_launches, err);
+    return rc == SRSCE_OK ? rc : fail(rc, err);
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
+int srsce_last_launch_count(void) { return g_launches; }
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Internal definitions shared by the host planner (srsce_plan.cc), the C ABI glue (srsce_api.cc)
+// and the CUDA kernels (srsce_kernels.cu).  Not part of the public ABI (include/srsce.h is).
+#pragma once
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include <vector_types.h>
+
+#include "srsce.h"
+
+namespace srsce {
+
+constexpr int kNRE = 12;              // resource elements per PRB
+constexpr int kThreads = 256;         // CTA size of the fused kernel
+constexpr int kWarps = kThreads / 32;
+constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
+constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
+constexpr int kMiscBytes = 6144;      // shared-memory slot of the kernel's small tables / reduction scratch
+
+// One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
+// a subcarrier at position p of PRB q takes pilots q*R+jl and q*R+jr of its CDM group
+// (jl = -1 / jr = R reach into the neighbouring PRB; the kernel clamps to [0, N-1], which
+// reproduces the flat extrapolation at both band edges) and alpha = (p - pos_l) / (pos_r - pos_l).
+struct LerpEntry {
+  int32_t jl;
+  int32_t jr;
+  float alpha;
+  int32_t pad;
+};
+
+struct HopDev {
+  int32_t band_sc0;        // 12 * PRBstart
+  int32_t band_sc1;        // 12 * (PRBstart + nPRBs)
+  int32_t start_symbol;
+  int32_t end_symbol;      // startSymbol + nAllocatedSymbols
+  int32_t n_dmrs;          // pilot symbols S of this hop
+  int32_t pilot_col0;      // first column of this hop in pilots[:, :, :]
+  int32_t pad0, pad1;
+  int32_t sym_idx[SRSCE_MAX_SYMBOLS];   // grid symbol of each pilot symbol
+  double t_dmrs[SRSCE_MAX_SYMBOLS];     // symbol_start_time (symbol units) at those symbols (:809-820)
+  double cfo_den;                       // 2*pi*n_samples*ceil(L/2)  (:410-426)
+};
+
+// Plain-old-data view of a plan passed to the kernel as a __grid_constant__ parameter.
+struct PlanDev {
+  int32_t n_sc, n_sym, n_layers, n_cdm;
+  int32_t re_per_prb;      // R
+  int32_t n_re;            // N = nPRBs * R pilots per CDM group
+  int32_t n_dmrs_total;    // S_total
+  int32_t n_hops;
+  int32_t smoothing, cfo_compensate, fill, cfo_defined;
+  int32_t n_taps, n_virtual;
+  int32_t fft_size;        // M
+  int32_t fft_regular;     // 1: M-point transform of the pilot vector (comb stride divides 4096); 0: zero-stuffed 4096
+  int32_t fft_layers;      // layers transformed together in the scratch buffer
+  int32_t fill_terms;      // T of the CNN operator
+  int32_t row_elems;       // n_sym * n_layers complex64 per subcarrier row of the output
+  int32_t vec;             // 2: float4 stores (row_elems even), 1: float2 stores
+  int32_t cols;            // row_elems / vec store slots per row
+  int32_t blend;           // CNN blend of the smoothed pilots active (ce_dl_cnn.py:712-717)
+  // shared-memory carve-up (byte offsets from the dynamic smem base)
+  int32_t off_h, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
+  float cnn_alpha;
+  float pad_f;
+  double scs_hz;
+  double vp_mx, vp_den;                   // create_virtual_pilots regression constants (:105-118)
+  double t_sym[SRSCE_MAX_SYMBOLS];        // symbol_start_time for the final CFO rotation (:922-929)
+  double taps[SRSCE_MAX_TAPS];
+  double norm_rsrp, norm_epre, norm_noise, ta_scale, ta_hop_div;  // :899-919
+  int32_t re_pos[2][kNRE];                // positions of the set bits of each CDM group's RE mask
+  LerpEntry lerp[2][kNRE];
+  HopDev hop[2];
+  // device tables (owned by the plan)
+  const float2* twiddle;                  // exp(+j*2*pi*k/4096), k < 4096
+  const int32_t* fill_idx;                // [n_cdm][band rows]           (CNN fill only)
+  const float* fill_coef;                 // [n_cdm][band rows][fill_terms]
+};
+
+struct Plan {
+  srsce_plan_desc desc;
+  PlanDev dev;
+  std::vector<double> taps;
+  std::vector<int32_t> fill_idx;      // host copy of the operator (lerp rows too, for the tests)
+  std::vector<float> fill_coef;
+  int fill_terms_host = 0;
+  int band_rows = 0;
+  int device = -1;                    // CUDA device the tables live on, -1: host-only plan
+  int ctas_per_sm = 0;                // occupancy of the selected kernel variant
+  int n_sms = 0;
+  void* d_twiddle = nullptr;
+  void* d_fill_idx = nullptr;
+  void* d_fill_coef = nullptr;
+  int64_t bytes_per_unit = 0;
+};
+
+// srsce_plan.cc
+int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err);
+void rc_taps(int stride, int n_rbs, std::vector<double>& taps);
+
+// srsce_kernels.cu
+int upload_plan(Plan& p, std::string& err);
+void release_plan(Plan& p);
+int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots,
+                    int pilot_share, double beta, void* out, double* scalars, int64_t n_units,
+                    void* stream, int* launches, std::string& err);
+int max_dynamic_smem();
+
+}  // namespace srsce

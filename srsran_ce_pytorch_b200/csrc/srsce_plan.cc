@@ -1,0 +1,442 @@
+// Host-side planner: everything about one estimator call that does not depend on the received
+// samples is computed once, here, in float64 -- raised-cosine taps, virtual-pilot regression
+// constants, CFO time tables, interpolation tables, the fixed-stencil "CNN" inpainting operator,
+// FFT geometry and the shared-memory carve-up of the fused kernel.
+//
+// Reference behaviour restated (all citations into /root/reference/src):
+//   get_rc_filter / _rcosdesign_normal      ce_rule_tensorized.py:184-234, :143-181
+//   virtual-pilot count                     :644-647
+//   create_virtual_pilots constants         :105-118
+//   CFO sample count, symbol start times    :410-426, :809-820
+//   fill_ch_est_cdm (linear)                :311-340
+//   ce_dl_cnn inpainting + low-pass         ce_dl_cnn.py:433-508, :274-295
+//   final normalisation                     ce_rule_tensorized.py:899-919
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+
+#include "srsce_internal.h"
+
+namespace srsce {
+
+static int popcount12(uint32_t m) {
+  int c = 0;
+  for (int k = 0; k < kNRE; ++k) c += (m >> k) & 1u;
+  return c;
+}
+
+// Raised cosine, roll-off 0.2, span n_rbs symbols at 10 samples/symbol; the centre tap and every
+// stride-th sample either side are kept and the result is normalised to unit sum.
+void rc_taps(int stride, int n_rbs, std::vector<double>& taps) {
+  const int sps = 10;
+  const double beta = 0.2;
+  const int half = (n_rbs * sps) / 2;
+  const int len = 2 * half + 1;
+  std::vector<double> h(len);
+  const double t0 = 1.0 / (2.0 * beta);
+  for (int k = 0; k < len; ++k) {
+    const double t = double(k - half) / double(sps);
+    double v;
+    if (fabs(fabs(t) - t0) < (1.0 / sps) * 1e-6) {
+      v = (M_PI * beta / 2.0) * sin(1.0 / (2.0 * beta));
+    } else {
+      const double sinc = (t == 0.0) ? 1.0 : sin(M_PI * t) / (M_PI * t);
+      v = sinc * cos(M_PI * beta * t) / (1.0 - (2.0 * beta * t) * (2.0 * beta * t));
+    }
+    h[k] = v;
+  }
+  const int reach = ((len / 2) / stride) * stride;
+  taps.clear();
+  double sum = 0.0;
+  for (int k = half - reach; k <= half + reach; k += stride) {
+    taps.push_back(h[k]);
+    sum += h[k];
+  }
+  for (double& v : taps) v /= sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The ce_dl_cnn "CNN": partial-convolution inpainting with the fixed stencil [.25 .5 .25],
+// known samples re-imposed every iteration, then two low-pass passes kept at the unknown
+// positions only.  It is linear in the known samples and -- because known samples are clamped
+// every iteration -- strictly local: an unknown run only ever sees the known sample(s) that
+// bound it.  So the operator is built exactly, run by run, by iterating the reference recurrence
+// in float64 on the run alone, and then composing with the two (reflect-padded) low-pass passes.
+// ---------------------------------------------------------------------------------------------
+typedef std::map<int, double> SparseRow;   // known-sample ordinal -> coefficient
+
+static void stencil_reflect(const std::vector<double>& v, std::vector<double>& out) {
+  const int n = int(v.size());
+  out.resize(n);
+  for (int i = 0; i < n; ++i) {
+    double l, r;
+    if (n == 1) {
+      l = r = v[0];
+    } else {
+      l = (i == 0) ? v[1] : v[i - 1];
+      r = (i == n - 1) ? v[n - 2] : v[i + 1];
+    }
+    out[i] = 0.25 * l + 0.5 * v[i] + 0.25 * r;
+  }
+}
+
+// Response of the unknown samples of a local segment to a unit value at local index `src`
+// (a known position of the segment), after n_iters iterations.
+static void inpaint_segment(const std::vector<char>& known, int src, int n_iters,
+                            std::vector<double>& resp) {
+  const int n = int(known.size());
+  std::vector<double> sparse(n, 0.0), cur, m(n), den, num, tmp(n);
+  sparse[src] = 1.0;
+  cur = sparse;
+  for (int i = 0; i < n; ++i) m[i] = known[i] ? 1.0 : 0.0;
+  for (int it = 0; it < std::max(1, n_iters); ++it) {
+    stencil_reflect(m, den);
+    for (int i = 0; i < n; ++i) tmp[i] = cur[i] * m[i];
+    stencil_reflect(tmp, num);
+    for (int i = 0; i < n; ++i) {
+      const double prop = num[i] / (den[i] + 1e-12);
+      if (den[i] > 1e-12 && m[i] < 1.0) m[i] = 1.0;
+      cur[i] = known[i] ? sparse[i] : prop;
+    }
+  }
+  resp = cur;
+}
+
+static void lowpass_rows(std::vector<SparseRow>& rows) {
+  const int n = int(rows.size());
+  if (n <= 2) return;
+  std::vector<SparseRow> out(n);
+  for (int i = 0; i < n; ++i) {
+    const int l = (i == 0) ? 1 : i - 1;
+    const int r = (i == n - 1) ? n - 2 : i + 1;
+    SparseRow& o = out[i];
+    for (const auto& kv : rows[l]) o[kv.first] += 0.25 * kv.second;
+    for (const auto& kv : rows[i]) o[kv.first] += 0.5 * kv.second;
+    for (const auto& kv : rows[r]) o[kv.first] += 0.25 * kv.second;
+  }
+  rows.swap(out);
+}
+
+static void cnn_operator_rows(const std::vector<char>& known, int n_iters, std::vector<SparseRow>& rows) {
+  const int n = int(known.size());
+  std::vector<int> ord(n, -1);
+  int n_known = 0;
+  for (int i = 0; i < n; ++i)
+    if (known[i]) ord[i] = n_known++;
+  rows.assign(n, SparseRow());
+  for (int i = 0; i < n; ++i)
+    if (known[i]) rows[i][ord[i]] = 1.0;
+  if (n_known == n) {                     // ce_dl_cnn.py:488-489: low-pass only, nothing re-imposed
+    lowpass_rows(rows);
+    lowpass_rows(rows);
+    return;
+  }
+  // unknown runs
+  int i = 0;
+  while (i < n) {
+    if (known[i]) { ++i; continue; }
+    int a = i;                            // first unknown of the run
+    int b = i;
+    while (b < n && !known[b]) ++b;       // one past the last unknown
+    const int lo = (a > 0) ? a - 1 : a;   // include the bounding known samples
+    const int hi = (b < n) ? b : b - 1;
+    std::vector<char> seg(known.begin() + lo, known.begin() + hi + 1);
+    std::vector<double> resp;
+    if (a > 0) {
+      inpaint_segment(seg, 0, n_iters, resp);
+      for (int k = a; k < b; ++k) rows[k][ord[a - 1]] += resp[k - lo];
+    }
+    if (b < n) {
+      inpaint_segment(seg, hi - lo, n_iters, resp);
+      for (int k = a; k < b; ++k) rows[k][ord[b]] += resp[k - lo];
+    }
+    i = b;
+  }
+  std::vector<SparseRow> lp = rows;
+  lowpass_rows(lp);
+  lowpass_rows(lp);
+  for (int k = 0; k < n; ++k)
+    if (!known[k]) rows[k].swap(lp[k]);
+}
+
+// Pack sparse rows as (first ordinal, T dense coefficients); the first ordinal is pulled back at
+// the band end so that first + T <= n_known and the kernel never has to clamp.
+static int pack_rows(const std::vector<SparseRow>& rows, int n_known, std::vector<int32_t>& idx,
+                     std::vector<float>& coef, int& terms) {
+  int t_max = 1;
+  for (const auto& r : rows) {
+    int lo = 1 << 30, hi = -1;
+    for (const auto& kv : r)
+      if (kv.second != 0.0) { lo = std::min(lo, kv.first); hi = std::max(hi, kv.first); }
+    if (hi >= 0) t_max = std::max(t_max, hi - lo + 1);
+  }
+  terms = std::max(terms, std::min(t_max, n_known));
+  return t_max;
+}
+
+static void emit_rows(const std::vector<SparseRow>& rows, int n_known, int terms,
+                      int32_t* idx, float* coef) {
+  for (size_t r = 0; r < rows.size(); ++r) {
+    int lo = 1 << 30;
+    for (const auto& kv : rows[r])
+      if (kv.second != 0.0) lo = std::min(lo, kv.first);
+    if (lo == (1 << 30)) lo = 0;
+    lo = std::max(0, std::min(lo, n_known - terms));
+    idx[r] = lo;
+    for (int t = 0; t < terms; ++t) coef[r * terms + t] = 0.f;
+    for (const auto& kv : rows[r])
+      if (kv.second != 0.0) coef[r * terms + (kv.first - lo)] = float(kv.second);
+  }
+}
+
+#define FAIL(code, ...)                                  \
+  do {                                                   \
+    char buf_[256];                                      \
+    snprintf(buf_, sizeof buf_, __VA_ARGS__);            \
+    err = buf_;                                          \
+    return code;                                         \
+  } while (0)
+
+int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
+  p.desc = d;
+  PlanDev& v = p.dev;
+  memset(&v, 0, sizeof v);
+
+  if (d.n_layers < 1 || d.n_layers > SRSCE_MAX_LAYERS)
+    FAIL(SRSCE_ERR_UNSUPPORTED, "n_layers=%d outside 1..%d", d.n_layers, SRSCE_MAX_LAYERS);
+  if (d.n_prb_grid < 1 || d.n_prb_grid * kNRE > SRSCE_TA_FFT)
+    FAIL(SRSCE_ERR_UNSUPPORTED, "grid of %d PRBs: n_sc must be in 12..4096 (time-alignment IFFT is 4096 points)", d.n_prb_grid);
+  if (d.n_sym < 1 || d.n_sym > SRSCE_MAX_SYMBOLS)
+    FAIL(SRSCE_ERR_UNSUPPORTED, "n_sym=%d outside 1..14", d.n_sym);
+  if (d.smoothing != SRSCE_SMOOTH_NONE && d.smoothing != SRSCE_SMOOTH_MEAN && d.smoothing != SRSCE_SMOOTH_FILTER)
+    FAIL(SRSCE_ERR_INVALID, "Unknown smoothing strategy %d.", d.smoothing);
+  if (d.fill != SRSCE_FILL_LINEAR && d.fill != SRSCE_FILL_CNN) FAIL(SRSCE_ERR_INVALID, "unknown fill mode %d", d.fill);
+  if (!(d.scs_hz > 0.0)) FAIL(SRSCE_ERR_INVALID, "scs must be positive");
+  if (d.cfo_compensate && d.n_cp < 14)
+    FAIL(SRSCE_ERR_INVALID, "config.CyclicPrefixDurations must have length >= 14 to match MATLAB code.");
+
+  const int L = d.n_layers, G = (L + 1) / 2;
+  const uint32_t sym_all = (d.n_sym >= 32) ? 0xffffffffu : ((1u << d.n_sym) - 1u);
+  const int n_hops = d.hop[1].dmrs_symbol_mask ? 2 : 1;
+  if (d.hop[0].dmrs_symbol_mask == 0) FAIL(SRSCE_ERR_INVALID, "hop 1 has no pilot symbol");
+  if (n_hops == 2) {
+    if (d.hop[0].dmrs_symbol_mask & d.hop[1].dmrs_symbol_mask) FAIL(SRSCE_ERR_ASSERT, "Hops should not overlap.");
+    if (d.hop[1].n_prbs != d.hop[0].n_prbs)
+      FAIL(SRSCE_ERR_INVALID, "both hops must span the same number of PRBs (one pilots tensor is split by symbol)");
+  }
+  const int R = popcount12(d.re_mask[0]);
+  if (R < 1) FAIL(SRSCE_ERR_INVALID, "DMRSREmask column 0 is empty");
+  for (int g = 0; g < G; ++g) {
+    if ((d.re_mask[g] & ~0xfffu) != 0) FAIL(SRSCE_ERR_INVALID, "DMRSREmask has more than 12 rows");
+    if (popcount12(d.re_mask[g]) != R)
+      FAIL(SRSCE_ERR_INVALID, "DMRSREmask columns must select the same number of REs per PRB");
+  }
+  int s_total = 0;
+  for (int h = 0; h < n_hops; ++h) {
+    const srsce_hop_desc& hd = d.hop[h];
+    if (hd.dmrs_symbol_mask & ~sym_all) FAIL(SRSCE_ERR_INVALID, "hop %d: pilot symbol outside the grid", h + 1);
+    if (hd.n_prbs < 1 || hd.prb_start < 0 || hd.prb_start + hd.n_prbs > d.n_prb_grid)
+      FAIL(SRSCE_ERR_INVALID, "hop %d: PRB range [%d, %d) outside the %d-PRB grid", h + 1, hd.prb_start,
+           hd.prb_start + hd.n_prbs, d.n_prb_grid);
+    if (hd.start_symbol < 0 || hd.n_alloc_symbols < 0 || hd.start_symbol + hd.n_alloc_symbols > d.n_sym)
+      FAIL(SRSCE_ERR_INVALID, "hop %d: allocated symbols [%d, %d) outside the grid", h + 1, hd.start_symbol,
+           hd.start_symbol + hd.n_alloc_symbols);
+    s_total += __builtin_popcount(hd.dmrs_symbol_mask);
+  }
+
+  const int n_prbs = d.hop[0].n_prbs;
+  const int N = n_prbs * R;
+  v.n_sc = d.n_prb_grid * kNRE;
+  v.n_sym = d.n_sym;
+  v.n_layers = L;
+  v.n_cdm = G;
+  v.re_per_prb = R;
+  v.n_re = N;
+  v.n_dmrs_total = s_total;
+  v.n_hops = n_hops;
+  v.smoothing = d.smoothing;
+  v.cfo_compensate = d.cfo_compensate ? 1 : 0;
+  v.fill = d.fill;
+  v.scs_hz = d.scs_hz;
+
+  // symbol start times in symbol units: cumsum([CP0, CP1 + 1, ... CP13 + 1])  (:809-820)
+  double cpd[SRSCE_MAX_SYMBOLS] = {0};
+  for (int t = 0; t < SRSCE_MAX_SYMBOLS && t < d.n_cp; ++t) cpd[t] = d.cp_ms[t] * d.scs_hz / 1000.0;
+  double t_sym[SRSCE_MAX_SYMBOLS] = {0};
+  if (d.n_cp >= 14) {
+    double acc = 0.0;
+    for (int t = 0; t < 14; ++t) {
+      acc += (t == 0) ? cpd[0] : cpd[t] + 1.0;
+      t_sym[t] = acc;
+    }
+  }
+  for (int t = 0; t < SRSCE_MAX_SYMBOLS; ++t) v.t_sym[t] = t_sym[t];
+
+  int col0 = 0;
+  for (int h = 0; h < n_hops; ++h) {
+    const srsce_hop_desc& hd = d.hop[h];
+    HopDev& hv = v.hop[h];
+    hv.band_sc0 = kNRE * hd.prb_start;
+    hv.band_sc1 = kNRE * (hd.prb_start + hd.n_prbs);
+    hv.start_symbol = hd.start_symbol;
+    hv.end_symbol = hd.start_symbol + hd.n_alloc_symbols;
+    hv.pilot_col0 = col0;
+    int s = 0;
+    for (int t = 0; t < d.n_sym; ++t)
+      if ((hd.dmrs_symbol_mask >> t) & 1u) {
+        hv.sym_idx[s] = t;
+        hv.t_dmrs[s] = t_sym[t < 14 ? t : 13];
+        ++s;
+      }
+    hv.n_dmrs = s;
+    col0 += s;
+    if (s >= 2) {
+      v.cfo_defined = 1;
+      // n_samples between the first two pilot symbols, CPs included (:410-421); a short CP
+      // vector is summed as far as it goes, like the reference's slice
+      double n_samp = double(hv.sym_idx[1] - hv.sym_idx[0]);
+      for (int t = hv.sym_idx[0] + 1; t <= hv.sym_idx[1] && t < d.n_cp && t < SRSCE_MAX_SYMBOLS; ++t) n_samp += cpd[t];
+      hv.cfo_den = 2.0 * M_PI * n_samp * double(G);
+    } else {
+      hv.cfo_den = 1.0;
+    }
+  }
+  if (v.cfo_compensate && v.cfo_defined && d.n_sym != 14)
+    FAIL(SRSCE_ERR_INVALID, "CFO compensation with >= 2 pilot symbols needs a 14-symbol grid (got %d)", d.n_sym);
+
+  // RE positions, interpolation table
+  for (int g = 0; g < G; ++g) {
+    int r = 0;
+    for (int k = 0; k < kNRE; ++k)
+      if ((d.re_mask[g] >> k) & 1u) v.re_pos[g][r++] = k;
+    for (int pos = 0; pos < kNRE; ++pos) {
+      int jr = 0;
+      while (jr < R && v.re_pos[g][jr] < pos) ++jr;          // searchsorted(..., side="left")
+      const int jl = jr - 1;
+      const int pr = (jr < R) ? v.re_pos[g][jr] : v.re_pos[g][0] + kNRE;
+      const int pl = (jl >= 0) ? v.re_pos[g][jl] : v.re_pos[g][R - 1] - kNRE;
+      LerpEntry& e = v.lerp[g][pos];
+      e.jl = jl;
+      e.jr = jr;
+      e.alpha = (float(pos) - float(pl)) / (float(pr) - float(pl));
+    }
+  }
+
+  // smoothing filter
+  v.n_taps = 0;
+  v.n_virtual = 0;
+  p.taps.clear();
+  if (d.smoothing == SRSCE_SMOOTH_FILTER) {
+    const int stride = kNRE / R;
+    if (stride < 1) FAIL(SRSCE_ERR_INVALID, "stride must be >= 1");
+    rc_taps(stride, std::min(3, n_prbs), p.taps);
+    if (int(p.taps.size()) > SRSCE_MAX_TAPS) FAIL(SRSCE_ERR_UNSUPPORTED, "filter longer than %d taps", SRSCE_MAX_TAPS);
+    v.n_taps = int(p.taps.size());
+    v.n_virtual = (n_prbs > 1) ? std::min(12, v.n_taps / 2) : R;
+    if (v.n_virtual > N) FAIL(SRSCE_ERR_UNSUPPORTED, "more virtual pilots than pilots");
+    for (int k = 0; k < v.n_taps; ++k) v.taps[k] = p.taps[k];
+    const int n = v.n_virtual;
+    if (n >= 2) {
+      double sx = 0.0, sxx = 0.0;
+      for (int k = 0; k < n; ++k) { sx += k; sxx += double(k) * k; }
+      const double nrm = sqrt(sxx);
+      v.vp_mx = sx / n;
+      v.vp_den = nrm * nrm - n * v.vp_mx * v.vp_mx;
+    }
+  }
+  v.blend = (d.fill == SRSCE_FILL_CNN && d.smoothing == SRSCE_SMOOTH_FILTER && d.cnn_alpha > 0.0) ? 1 : 0;
+  v.cnn_alpha = float(std::max(0.0, std::min(1.0, d.cnn_alpha)));
+
+  // time alignment: the positions of the LAST CDM group are used for every layer (:674-675).
+  // If that comb is regular with a stride s that divides 4096, |IFFT_4096(zero-stuffed)| equals the
+  // tiled |IFFT_{4096/s}(pilots)| (position offset only adds a linear phase), so a short transform suffices.
+  {
+    const int* pos = v.re_pos[G - 1];
+    const int s = kNRE / R;
+    bool regular = (R * s == kNRE) && (SRSCE_TA_FFT % s == 0);
+    for (int r = 1; r < R && regular; ++r) regular = (pos[r] - pos[r - 1] == s);
+    if (regular && N <= SRSCE_TA_FFT / s) {
+      v.fft_regular = 1;
+      v.fft_size = SRSCE_TA_FFT / s;
+    } else {
+      v.fft_regular = 0;
+      v.fft_size = SRSCE_TA_FFT;
+    }
+    v.fft_layers = std::max(1, std::min(L, 4096 / v.fft_size));
+  }
+
+  // normalisation (:899-919)
+  {
+    const double n_pil = double(n_prbs) * R * s_total;
+    v.norm_rsrp = 1.0 / (n_pil * L);
+    v.norm_epre = 1.0 / n_pil;
+    v.norm_noise = 1.0 / (double(G) * n_pil - 1.0);
+    v.ta_scale = 1.0 / double(SRSCE_TA_FFT) / d.scs_hz;
+    v.ta_hop_div = (n_hops == 2) ? 2.0 : 1.0;
+  }
+
+  // output row geometry
+  v.row_elems = d.n_sym * L;
+  v.vec = (v.row_elems % 2 == 0) ? 2 : 1;
+  v.cols = v.row_elems / v.vec;
+
+  // fill operator.  Host copy always (tests); the device copy is only used by the CNN fill.
+  p.band_rows = kNRE * n_prbs;
+  {
+    std::vector<std::vector<SparseRow>> all(G);
+    int terms = 1;
+    for (int g = 0; g < G; ++g) {
+      std::vector<SparseRow>& rows = all[g];
+      if (d.fill == SRSCE_FILL_CNN) {
+        std::vector<char> known(p.band_rows);
+        for (int r = 0; r < p.band_rows; ++r) known[r] = (d.re_mask[g] >> (r % kNRE)) & 1u;
+        cnn_operator_rows(known, std::max(6, p.band_rows / 8), rows);
+      } else {
+        rows.assign(p.band_rows, SparseRow());
+        for (int r = 0; r < p.band_rows; ++r) {
+          const LerpEntry& e = v.lerp[g][r % kNRE];
+          const int q = r / kNRE;
+          const int il = std::max(0, std::min(N - 1, q * R + e.jl));
+          const int ir = std::max(0, std::min(N - 1, q * R + e.jr));
+          rows[r][il] += 1.0 - double(e.alpha);
+          rows[r][ir] += double(e.alpha);
+        }
+      }
+      std::vector<int32_t> dummy_i;
+      std::vector<float> dummy_f;
+      pack_rows(rows, N, dummy_i, dummy_f, terms);
+    }
+    if (d.fill == SRSCE_FILL_CNN && terms > kMaxFillTerms)
+      FAIL(SRSCE_ERR_UNSUPPORTED, "CNN operator rows span %d pilots (max %d)", terms, kMaxFillTerms);
+    p.fill_terms_host = terms;
+    p.fill_idx.assign(size_t(G) * p.band_rows, 0);
+    p.fill_coef.assign(size_t(G) * p.band_rows * terms, 0.f);
+    for (int g = 0; g < G; ++g)
+      emit_rows(all[g], N, terms, &p.fill_idx[size_t(g) * p.band_rows], &p.fill_coef[size_t(g) * p.band_rows * terms]);
+    v.fill_terms = (d.fill == SRSCE_FILL_CNN) ? terms : 2;
+  }
+
+  // shared memory: smoothed pilots of every hop | raw pilots + virtual pilots, later FFT scratch,
+  // later the warps' expansion tiles | small tables and reduction scratch
+  {
+    const int h_elems = n_hops * N * L;
+    int ext = (N + 2 * v.n_virtual) * L;
+    ext = std::max(ext, v.fft_layers * v.fft_size);
+    ext = std::max(ext, kWarps * kTileRows * L * n_hops + kWarps * kTileRows / 2);
+    v.ext_elems = ext;
+    v.off_h = 0;
+    v.off_ext = v.off_h + ((h_elems * 8 + 15) / 16) * 16;
+    v.off_tile = v.off_ext;
+    v.off_misc = v.off_ext + ((ext * 8 + 15) / 16) * 16;
+    v.smem_bytes = v.off_misc + kMiscBytes;
+    if (v.smem_bytes > 227 * 1024)
+      FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
+  }
+
+  p.bytes_per_unit = 8LL * (int64_t(G) * N * s_total + int64_t(N) * s_total * L + int64_t(v.n_sc) * d.n_sym * L) + 48;
+  return SRSCE_OK;
+}
+
+}  // namespace srsce

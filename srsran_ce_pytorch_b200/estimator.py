@@ -1,0 +1,223 @@
+"""Host side of the estimator: reference-compatible entry points over the C ABI.
+
+``srs_channel_estimator`` has the signature, argument meaning, return tuple and error behaviour of
+the reference function of the same name (/root/reference src/ce_rule_tensorized.py:745-937; the
+same in ce_rule_baseline.py:761 and ce_dl_cnn.py:802) but only accepts CUDA tensors: everything is
+computed by the fused sm_100a kernel in ``libsrsce.so``.  ``srs_channel_estimator_batched`` is the
+same call over many independent units (slot x UE x rx antenna) in one launch.
+
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib
+
+NRE = 12
+_SCALAR_FIELDS = ("noise_est", "rsrp", "epre", "time_alignment", "cfo_hz", "cfo_valid")
+
+
+def _host(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def _hop_desc(hop, n_sym: int, n_prb_grid: int, tag: str) -> Tuple[_lib.HopDesc, Optional[np.ndarray]]:
+    """HopConfig (reference field names, :13-21) -> ABI hop descriptor + its RE mask [12, n_cdm]."""
+    d = _lib.HopDesc()
+    sym = _host(hop.DMRSsymbols).astype(bool).reshape(-1)
+    if sym.size == 0 or not sym.any():
+        return d, None                                    # "hop absent" sentinel (validate_all.py:449-457)
+    if sym.size != n_sym:
+        raise IndexError(f"{tag}.DMRSsymbols has {sym.size} entries for a grid of {n_sym} symbols")
+    prbs = _host(hop.maskPRBs).astype(bool).reshape(-1)
+    if prbs.size != n_prb_grid:
+        raise IndexError(f"{tag}.maskPRBs has {prbs.size} entries for a grid of {n_prb_grid} PRBs")
+    start, n = int(hop.PRBstart), int(hop.nPRBs)
+    want = np.zeros_like(prbs)
+    want[max(0, start):max(0, start + n)] = True
+    if not np.array_equal(prbs, want):
+        raise ValueError(f"{tag}.maskPRBs must be exactly the contiguous range [PRBstart, PRBstart+nPRBs)")
+    mask = 0
+    for t in np.flatnonzero(sym):
+        mask |= 1 << int(t)
+    d.dmrs_symbol_mask = mask
+    d.prb_start, d.n_prbs = start, n
+    d.start_symbol, d.n_alloc_symbols = int(hop.startSymbol), int(hop.nAllocatedSymbols)
+    rm = _host(hop.DMRSREmask).astype(bool)
+    if rm.ndim == 1:
+        rm = rm.reshape(NRE, -1)
+    if rm.shape[0] != NRE:
+        raise ValueError(f"{tag}.DMRSREmask must have 12 rows")
+    return d, rm
+
+
+class Plan:
+    """Data-independent part of a call (geometry, filter taps, operator tables), created once and
+    cached.  Thin owner of an ``srsce_plan*``."""
+
+    def __init__(self, desc: _lib.PlanDesc):
+        self.desc = desc
+        handle = C.c_void_p()
+        _lib.raise_for(lib.srsce_plan_create(C.byref(desc), C.byref(handle)))
+        self._h = handle
+        info = _lib.PlanInfo()
+        _lib.raise_for(lib.srsce_plan_query(self._h, C.byref(info)))
+        self.info = info
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and lib is not None:                      # lib is None during interpreter shutdown
+            lib.srsce_plan_destroy(h)
+
+    # ---- host tables (tests of the host logic; no device needed)
+    def tables(self):
+        i = self.info
+        taps = np.zeros(max(1, i.n_taps), dtype=np.float64)
+        rows = NRE * self.desc.hop[0].n_prbs
+        idx = np.zeros((i.n_cdm, rows), dtype=np.int32)
+        coef = np.zeros((i.n_cdm, rows, i.fill_terms), dtype=np.float32)
+        _lib.raise_for(lib.srsce_plan_tables(self._h, taps.ctypes.data, idx.ctypes.data, coef.ctypes.data))
+        return taps[:i.n_taps], idx, coef
+
+    # ---- the compute call
+    def estimate(self, rx: torch.Tensor, pilots: torch.Tensor, beta: float, pilot_share: int = 1,
+                 out: Optional[torch.Tensor] = None, scalars: Optional[torch.Tensor] = None):
+        """rx [B, n_sc, n_sym] complex64 CUDA (any strides), pilots [B // pilot_share, n_re, S, L]
+        complex64 contiguous.  Returns (ch_est [B, n_sc, n_sym, L], scalars [B, 6] float64)."""
+        i = self.info
+        if not rx.is_cuda or not pilots.is_cuda:
+            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
+        if rx.dtype != torch.complex64 or pilots.dtype != torch.complex64:
+            raise TypeError("rx and pilots must be complex64")
+        if rx.dim() != 3 or tuple(rx.shape[1:]) != (i.n_sc, i.n_sym):
+            raise IndexError(f"received grid shape {tuple(rx.shape)} != [B, {i.n_sc}, {i.n_sym}]")
+        n_units = int(rx.shape[0])
+        if pilot_share < 1 or n_units % pilot_share:
+            raise ValueError("number of units must be a multiple of pilot_share")
+        want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
+        if tuple(pilots.shape) != want:
+            raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
+        if not pilots.is_contiguous():
+            pilots = pilots.contiguous()
+        if out is None:
+            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=rx.device)
+        elif tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers) or not out.is_contiguous() \
+                or out.dtype != torch.complex64 or out.device != rx.device:
+            raise ValueError("out must be a contiguous complex64 [B, n_sc, n_sym, L] tensor on rx.device")
+        if scalars is None:
+            scalars = torch.empty((n_units, 6), dtype=torch.float64, device=rx.device)
+        elif tuple(scalars.shape) != (n_units, 6) or not scalars.is_contiguous() or scalars.dtype != torch.float64:
+            raise ValueError("scalars must be a contiguous float64 [B, 6] tensor")
+        strides = (C.c_int64 * 3)(*rx.stride())
+        with torch.cuda.device(rx.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.raise_for(lib.srsce_estimate(self._h, rx.data_ptr(), strides, pilots.data_ptr(), int(pilot_share),
+                                              float(beta), out.data_ptr(), scalars.data_ptr(), n_units,
+                                              C.c_void_p(stream)))
+        return out, scalars
+
+
+_PLANS: dict = {}
+_PLANS_LOCK = threading.Lock()
+
+
+def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fill: str = "linear") -> Plan:
+    """Build (or fetch from the cache) the plan for HopConfig x2 + EstimatorConfig + tensor shapes."""
+    desc = _lib.PlanDesc()
+    desc.n_prb_grid, desc.n_sym, desc.n_layers = int(n_prb_grid), int(n_sym), int(n_layers)
+    smoothing = getattr(config, "Smoothing", None)
+    smoothing = "filter" if smoothing is None else str(smoothing)       # :785-787
+    if smoothing not in _lib.SMOOTH:
+        raise ValueError(f"Unknown smoothing strategy {smoothing}.")    # :668
+    desc.smoothing = _lib.SMOOTH[smoothing]
+    desc.cfo_compensate = 1 if bool(getattr(config, "CFOCompensate", True)) else 0   # :803-806
+    desc.fill = _lib.FILL_CNN if fill == "cnn" else _lib.FILL_LINEAR
+    alpha = getattr(config, "CNNSmoothingAlpha", 0.0) if fill == "cnn" else 0.0      # ce_dl_cnn.py:864-867
+    desc.cnn_alpha = float(alpha or 0.0)
+    desc.scs_hz = float(config.scs)
+    cp = _host(config.CyclicPrefixDurations).astype(np.float64).reshape(-1)
+    desc.n_cp = int(min(cp.size, _lib.MAX_SYMBOLS))
+    for k in range(desc.n_cp):
+        desc.cp_ms[k] = float(cp[k])
+    h1, rm1 = _hop_desc(hop1, n_sym, n_prb_grid, "hop1")
+    h2, rm2 = _hop_desc(hop2, n_sym, n_prb_grid, "hop2")
+    if rm1 is None:
+        raise ValueError("hop1 has no pilot symbol")
+    if rm2 is not None:
+        if h1.dmrs_symbol_mask & h2.dmrs_symbol_mask:
+            raise AssertionError("Hops should not overlap.")                                    # :862
+        assert rm1.shape == rm2.shape and np.array_equal(rm1, rm2), \
+            "The DM-RS mask should be the same for the two hops."                               # :869
+    n_cdm = (n_layers + 1) // 2
+    if rm1.shape[1] < n_cdm:
+        raise IndexError(f"DMRSREmask has {rm1.shape[1]} columns, {n_cdm} CDM groups needed")
+    for g in range(n_cdm):
+        desc.re_mask[g] = int(sum(1 << k for k in range(NRE) if rm1[k, g]))
+    desc.hop[0], desc.hop[1] = h1, h2
+    key = bytes(desc)
+    with _PLANS_LOCK:
+        plan = _PLANS.get(key)
+        if plan is None:
+            plan = _PLANS[key] = Plan(desc)
+    return plan
+
+
+def _as_c64(x, device=None) -> torch.Tensor:
+    t = torch.as_tensor(x, device=device)
+    if t.dtype != torch.complex64:
+        t = t.to(torch.complex64)                       # real inputs are promoted like the reference (:773-779)
+    return t
+
+
+def srs_channel_estimator_batched(received_rg, pilots, beta_dmrs, hop1, hop2, config, *, fill: str = "linear",
+                                  pilot_share: Optional[int] = None, out=None, scalars=None):
+    """Many independent reference calls in one launch.
+
+    received_rg [B, n_sc, n_sym], pilots [U, n_re, n_dmrs_total, L] with B = U * pilot_share (the
+    pilot_share consecutive units of a UE -- its rx antennas -- share one pilot block).
+    Returns (channel_est_rg [B, n_sc, n_sym, L] complex64, scalars [B, 6] float64 with columns
+    noise_est, rsrp, epre, time_alignment, cfo_hz, cfo_valid).  Unit b equals the reference called
+    on (received_rg[b], pilots[b // pilot_share])."""
+    rx = _as_c64(received_rg)
+    pil = _as_c64(pilots, device=rx.device)
+    if rx.dim() != 3 or pil.dim() != 4:
+        raise IndexError("expected received_rg [B, n_sc, n_sym] and pilots [U, n_re, n_dmrs, L]")
+    if rx.shape[1] % NRE:
+        raise IndexError("n_sc must be a multiple of 12")
+    if pilot_share is None:
+        if pil.shape[0] == 0 or rx.shape[0] % pil.shape[0]:
+            raise ValueError("B must be a multiple of the number of pilot blocks")
+        pilot_share = rx.shape[0] // pil.shape[0]
+    plan = make_plan(rx.shape[1] // NRE, rx.shape[2], pil.shape[3], hop1, hop2, config, fill)
+    return plan.estimate(rx, pil, float(beta_dmrs), pilot_share, out=out, scalars=scalars)
+
+
+def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *, fill: str = "linear"):
+    """Drop-in for the reference ``srs_channel_estimator`` (one received grid, one UE).
+
+    Returns (channel_est_rg [n_sc, n_sym, L] complex64, noise_est, rsrp, epre, time_alignment
+    float64 0-dim, cfo_hz float64 0-dim or an empty (0,) tensor when no hop has two pilot symbols),
+    all on ``received_rg.device`` and without a host synchronisation."""
+    rx = _as_c64(received_rg)
+    pil = _as_c64(pilots, device=rx.device)
+    if rx.dim() != 2 or pil.dim() != 3:
+        raise IndexError("expected received_rg [n_sc, n_sym] and pilots [n_re, n_dmrs, L]")
+    if rx.shape[0] % NRE:
+        raise IndexError("n_sc must be a multiple of 12")
+    plan = make_plan(rx.shape[0] // NRE, rx.shape[1], pil.shape[2], hop1, hop2, config, fill)
+    grid, sc = plan.estimate(rx.unsqueeze(0), pil.unsqueeze(0), float(beta_dmrs), 1)
+    cfo = sc[0, 4] if plan.info.cfo_defined else torch.empty((0,), dtype=torch.float64, device=rx.device)
+    return grid[0], sc[0, 0], sc[0, 1], sc[0, 2], sc[0, 3], cfo
+
+
+def unpack_scalars(scalars: torch.Tensor) -> dict:
+    return {name: scalars[:, k] for k, name in enumerate(_SCALAR_FIELDS)}

@@ -1,0 +1,163 @@
+"""Parity of the CUDA path (through the drop-in entry points, i.e. through the C ABI) with
+  * outputs of the unmodified reference stored in tests/golden (all three variants), and
+  * the numpy oracle on fresh seeded inputs, batched,
+plus size-independent properties at BASELINE.json's full config-2 size.
+Floating point: tolerances are in tests/tolerances.py (grid max-rel 1e-5 and NMSE 1e-12 gates)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ce_oracle
+from tests import tolerances as tol
+from tests.golden_io import case_names, load_case
+
+pytestmark = pytest.mark.gpu
+NAMES = case_names()
+
+
+def _dev(x):
+    return torch.as_tensor(x).cuda()
+
+
+def _scalars(out):
+    cfo = out[5]
+    return [float(out[1]), float(out[2]), float(out[3]), float(out[4]), float(cfo) if cfo.numel() else None]
+
+
+def _ta_margin(c, variant):
+    diag = {}
+    ce_oracle.estimate(c["rx"], c["pilots"], c["beta"], c["hop1"], c["hop2"], c["cfg"],
+                       fill="tensorized" if variant != "cnn" else "tensorized", diagnostics=diag)
+    return diag["ta_margin"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_rule_estimator_matches_reference(name):
+    """ce_rule_tensorized / ce_rule_baseline drop-ins vs the stored reference outputs."""
+    from srsran_ce_pytorch_b200.compat import ce_rule_baseline, ce_rule_tensorized
+    c = load_case(name)
+    margin = _ta_margin(c, "tensorized")
+    for variant, mod in (("tensorized", ce_rule_tensorized), ("baseline", ce_rule_baseline)):
+        if f"{variant}_grid" not in c["ref"]:
+            continue
+        out = mod.srs_channel_estimator(_dev(c["rx"]), _dev(c["pilots"]), c["beta"], c["hop1"], c["hop2"], c["cfg"])
+        assert out[0].dtype == torch.complex64 and out[1].dtype == torch.float64 and out[0].is_cuda
+        mx, nmse = tol.grid_errors(out[0].cpu().numpy(), c["ref"][f"{variant}_grid"])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (name, variant, mx, nmse)
+        tol.check_scalars(_scalars(out), c["ref"][f"{variant}_scalars"], float(c["cfg"].scs), margin,
+                          tag=f"{name}/{variant}")
+
+
+@pytest.mark.parametrize("name", [n for n in NAMES])
+def test_cnn_estimator_matches_reference(name):
+    from srsran_ce_pytorch_b200.compat import ce_dl_cnn
+    c = load_case(name)
+    if "cnn_grid" not in c["ref"]:
+        pytest.skip("no ce_dl_cnn output stored for this case")
+    out = ce_dl_cnn.srs_channel_estimator(_dev(c["rx"]), _dev(c["pilots"]), c["beta"], c["hop1"], c["hop2"], c["cfg"])
+    mx, nmse = tol.grid_errors(out[0].cpu().numpy(), c["ref"]["cnn_grid"])
+    assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (name, mx, nmse)
+    tol.check_scalars(_scalars(out), c["ref"]["cnn_scalars"], float(c["cfg"].scs), _ta_margin(c, "cnn"),
+                      tag=f"{name}/cnn")
+
+
+BATCH_CASES = [
+    # grid, start, n_prbs, symbols, pattern, layers, smoothing, cfo, hop2 (start, symbols), pilot_share, symbol_major
+    (52, 5, 12, [2, 11], "comb2", 2, "filter", True, None, 2, False),
+    (52, 0, 52, [3], "comb4", 4, "filter", True, None, 4, True),
+    (106, 10, 24, [2, 7, 11], "type2", 3, "filter", True, None, 1, False),
+    (52, 2, 8, [1, 3], "comb4", 4, "mean", True, (30, [8, 10]), 2, True),
+    (52, 2, 8, [2], "comb6", 2, "none", False, (40, [9]), 1, False),
+    (25, 0, 25, [0, 5, 10], "dense", 1, "filter", False, None, 1, False),
+    (52, 7, 3, [4, 9], "comb3", 2, "filter", True, None, 3, False),
+    (52, 7, 2, [4], "comb12", 1, "filter", True, None, 1, False),
+    (52, 7, 1, [4, 6], "comb6", 1, "filter", True, None, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", BATCH_CASES, ids=[f"b{i}" for i in range(len(BATCH_CASES))])
+@pytest.mark.parametrize("fill", ["linear", "cnn"])
+def test_batched_units_match_oracle(case, fill):
+    """batched[b] == oracle(rx[b], pilots[b // share]) for every unit of a seeded batch."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    grid, start, n, syms, pat, L, sm, cfo, h2, share, sym_major = case
+    hop1 = synth.make_hop(grid, start, n, syms, pat, (L + 1) // 2)
+    hop2 = synth.no_hop() if h2 is None else synth.make_hop(grid, h2[0], n, h2[1], pat, (L + 1) // 2)
+    cfg = synth.make_config(30e3, sm, cfo)
+    n_units = 6 * share
+    data = synth.make_units(hop1, hop2, cfg, L, n_units, pilot_share=share, seed=99, device="cuda",
+                            symbol_major=sym_major, beta=1.25)
+    out, sc = estimator.srs_channel_estimator_batched(data["rx"], data["pilots"], data["beta"], hop1, hop2, cfg,
+                                                      fill=fill, pilot_share=share)
+    out, sc = out.cpu().numpy(), sc.cpu().numpy()
+    rx, pil = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+    for b in range(n_units):
+        diag = {}
+        want = ce_oracle.estimate(rx[b], pil[b // share], data["beta"], hop1, hop2, cfg,
+                                  fill="cnn" if fill == "cnn" else "tensorized", diagnostics=diag)
+        mx, nmse = tol.grid_errors(out[b], want[0])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (case, fill, b, mx, nmse)
+        got = [sc[b, 0], sc[b, 1], sc[b, 2], sc[b, 3], sc[b, 4] if sc[b, 5] else None]
+        tol.check_scalars(got, want[1:], float(cfg.scs), diag["ta_margin"], tag=f"{case}/{fill}/{b}")
+
+
+def _config2(n_units, syms=(13,), seed=1234, share=4):
+    from srsran_ce_pytorch_b200 import synth
+    hop1 = synth.make_hop(273, 0, 273, list(syms), "comb4", 2)
+    cfg = synth.make_config(30e3, "filter", True)
+    data = synth.make_units(hop1, synth.no_hop(), cfg, 4, n_units, pilot_share=share, seed=seed, device="cuda")
+    return hop1, synth.no_hop(), cfg, data
+
+
+def test_config2_full_size_properties():
+    """BASELINE config 2 (273 PRB, 4 ports, 4 rx, comb-4, 64 UEs = 256 units): properties that need no
+    oracle run -- batch independence (bit exact), homogeneity under a complex gain, and a spot check of
+    a few units against the oracle."""
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(256)
+    out, sc = estimator.srs_channel_estimator_batched(data["rx"], data["pilots"], 1.0, hop1, hop2, cfg, pilot_share=4)
+    assert out.shape == (256, 3276, 14, 4) and torch.isfinite(torch.view_as_real(out)).all()
+    # batch independence: a sub-batch gives bit-identical results
+    sub, sc_sub = estimator.srs_channel_estimator_batched(data["rx"][64:72], data["pilots"][16:18], 1.0, hop1, hop2,
+                                                          cfg, pilot_share=4)
+    assert torch.equal(sub, out[64:72]) and torch.equal(sc_sub, sc[64:72])
+    # homogeneity: rx * g  ->  grid * g, rsrp/epre/noise * |g|^2, same time alignment
+    g = complex(0.6, -1.7)
+    out_g, sc_g = estimator.srs_channel_estimator_batched(data["rx"][:16] * g, data["pilots"][:4], 1.0, hop1, hop2,
+                                                          cfg, pilot_share=4)
+    mx, nmse = tol.grid_errors(out_g.cpu().numpy(), (out[:16] * g).cpu().numpy())
+    assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (mx, nmse)
+    assert torch.allclose(sc_g[:, :3], sc[:16, :3] * abs(g) ** 2, rtol=1e-5, atol=0)
+    assert torch.equal(sc_g[:, 3], sc[:16, 3])
+    # spot check against the oracle
+    rx, pil = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+    for b in (0, 101, 255):
+        diag = {}
+        want = ce_oracle.estimate(rx[b], pil[b // 4], 1.0, hop1, hop2, cfg, diagnostics=diag)
+        mx, nmse = tol.grid_errors(out[b].cpu().numpy(), want[0])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (b, mx, nmse)
+        s = sc[b].cpu().numpy()
+        tol.check_scalars([s[0], s[1], s[2], s[3], s[4] if s[5] else None], want[1:], 30e3, diag["ta_margin"], tag=f"cfg2/{b}")
+
+
+def test_symbol_major_input_is_equivalent():
+    """The batched entry point takes any strides: a [B, n_sym, n_sc] grid viewed as [B, n_sc, n_sym]
+    gives bit-identical results to the reference layout."""
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(8, syms=(3, 10))
+    a, sa = estimator.srs_channel_estimator_batched(data["rx"], data["pilots"], 1.0, hop1, hop2, cfg, pilot_share=4)
+    rx_t = data["rx"].transpose(1, 2).contiguous().transpose(1, 2)
+    assert rx_t.stride() != data["rx"].stride()
+    b, sb = estimator.srs_channel_estimator_batched(rx_t, data["pilots"], 1.0, hop1, hop2, cfg, pilot_share=4)
+    assert torch.equal(a, b) and torch.equal(sa, sb)
+
+
+def test_empty_batch_and_return_types():
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(4)
+    out, sc = estimator.srs_channel_estimator_batched(data["rx"][:0], data["pilots"][:0], 1.0, hop1, hop2, cfg,
+                                                      pilot_share=4)
+    assert out.shape == (0, 3276, 14, 4) and sc.shape == (0, 6)
+    one = estimator.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, hop2, cfg)
+    assert one[0].shape == (3276, 14, 4) and one[5].shape == (0,) and one[5].dtype == torch.float64
+    assert all(t.dim() == 0 and t.dtype == torch.float64 for t in one[1:5])
