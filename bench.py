@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the estimator hot path (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (per GPU, fixed as N grows -> weak scaling): 273 PRB / 30 kHz full-band comb-4 pilots,
+4 ports (2 CDM groups x OCC-2), 4 rx antennas x 64 UEs = 256 units per slot, `--slots` slots per
+step (default 64 -> 16 384 units per step), one pilot symbol, 14-symbol output grid, raised-cosine
+smoothing, CFO compensation switched on.  One step = one launch of the fused kernel over the
+step's units (+ the NCCL gather of the scalar table when N > 1).  Synthetic data, seeded.
+
+`value`     channel estimates/s (units x 4 ports), device-timed, inputs resident in HBM.
+`e2e`       the same metric through the host-buffer entry point (pinned host tensors in, dense
+            grids + scalars back in host memory, copies inside the timed region).
+`roofline`  algorithmic HBM bytes of the fused kernel / its CUDA-event duration vs the measured
+            copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` the numpy oracle port on all host cores (rank 0, N = 1), bounded sample.
+`--impl reference` times that CPU path alone, same metric / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "SRS channel estimates/sec (UE x port x rx-ant) at 273 PRB"
+UNIT = "estimates/s"
+N_PRB, N_SYM, LAYERS, RX_ANT, UES, PILOT_SYMBOLS = 273, 14, 4, 4, 64, (13,)
+UNITS_PER_SLOT = RX_ANT * UES
+
+
+def workload_config(slots, e2e_slots=None):
+    cfg = {"workload": "config2: ce_rule_tensorized batched, 273 PRB 30 kHz, 4 ports, 4 rx antennas, comb-4, "
+                       "64 UEs per slot, 1 pilot symbol, 14-symbol grid, filter smoothing, CFO compensation on",
+           "units_per_step": slots * UNITS_PER_SLOT, "slots_per_step": slots, "estimates_per_unit": LAYERS,
+           "l2_policy": "inputs+outputs per step (>= 7 GB) exceed the 126 MB L2; no flush needed"}
+    if e2e_slots is not None:
+        cfg["e2e_units_per_step"] = e2e_slots * UNITS_PER_SLOT
+    return cfg
+
+
+def geometry():
+    from srsran_ce_pytorch_b200 import synth
+    hop1 = synth.make_hop(N_PRB, 0, N_PRB, list(PILOT_SYMBOLS), "comb4", 2)
+    return hop1, synth.no_hop(), synth.make_config(30e3, "filter", True)
+
+
+def algorithmic_bytes_per_unit():
+    """8 * [G*N*S (rx pilot REs) + N*S*L/A (pilots shared by the A antennas) + n_sc*n_sym*L] + 48."""
+    n, s, g = N_PRB * 3, len(PILOT_SYMBOLS), 2
+    return 8 * (g * n * s + n * s * LAYERS // RX_ANT + 12 * N_PRB * N_SYM * LAYERS) + 48
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm (oracle port on all host cores)
+# --------------------------------------------------------------------------------------------
+def cpu_pool(n_distinct=16):
+    from oracle import ce_oracle, cpu_bench
+    from srsran_ce_pytorch_b200 import synth
+    hop1, hop2, cfg = geometry()
+    d = synth.make_units(hop1, hop2, cfg, LAYERS, n_distinct, pilot_share=RX_ANT, seed=4321)
+    return cpu_bench.OraclePool(d["rx"].numpy(), d["pilots"].numpy(), RX_ANT, 1.0, ce_oracle.hop_from_any(hop1),
+                                ce_oracle.HopSpec.absent(), ce_oracle.est_from_any(cfg))
+
+
+def cpu_baseline(units_per_worker=96):
+    pool = cpu_pool()
+    try:
+        pool.run(4)
+        wall = pool.run(units_per_worker)
+    finally:
+        pool.close()
+    units = pool.cores * units_per_worker
+    return {"value": LAYERS * units / wall, "unit": UNIT, "cores": pool.cores, "kind": "port",
+            "sample": f"{units} units of the bench workload ({units_per_worker} per worker, 1 thread each, "
+                      f"{wall:.2f} s wall); numpy port of ce_rule_tensorized (2.9x faster than the torch "
+                      f"reference in the build container)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pool = cpu_pool()
+    upw = 24
+    try:
+        for _ in range(max(1, args.warmup)):
+            pool.run(4)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.run(upw)
+        wall = time.perf_counter() - t0
+    finally:
+        pool.close()
+    units = pool.cores * upw * args.steps
+    value = LAYERS * units / wall
+    cfg = workload_config(args.slots)
+    cfg["reference_step"] = f"{pool.cores * upw} units per step (bounded sample of the step's units)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "complex64 (f32) data, f64 scalars", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pool.cores, "kind": "port",
+                         "sample": f"{units} units, {upw} per worker per step, 1 thread per worker"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of one GPU every ~5 ms through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.max_mhz, self.stop_flag, self.err = index, [], 0, None, False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                time.sleep(0.005)
+        except Exception as e:  # noqa: BLE001 -- the bench must not die on a monitoring problem
+            self.err = repr(e)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"],
+                "samples": len(s), **({"error": self.err} if self.err else {})}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except (ValueError, IndexError):
+            return local
+    return local
+
+
+def make_step_inputs(slots, seed0, device):
+    import torch
+    from srsran_ce_pytorch_b200 import synth
+    hop1, hop2, cfg = geometry()
+    n = slots * UNITS_PER_SLOT
+    rx = torch.empty((n, 12 * N_PRB, N_SYM), dtype=torch.complex64, device=device)
+    pil = torch.empty((n // RX_ANT, N_PRB * 3, len(PILOT_SYMBOLS), LAYERS), dtype=torch.complex64, device=device)
+    for s in range(slots):
+        d = synth.make_units(hop1, hop2, cfg, LAYERS, UNITS_PER_SLOT, pilot_share=RX_ANT, seed=seed0 + s, device=device)
+        rx[s * UNITS_PER_SLOT:(s + 1) * UNITS_PER_SLOT] = d["rx"]
+        pil[s * UES:(s + 1) * UES] = d["pilots"]
+    return rx, pil
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()                     # before CUDA is touched: workers are spawned, not forked
+
+    from srsran_ce_pytorch_b200 import _lib, estimator, sharding
+    from srsran_ce_pytorch_b200.hostio import HostPipeline
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    hop1, hop2, cfg = geometry()
+    plan = estimator.make_plan(N_PRB, N_SYM, LAYERS, hop1, hop2, cfg)
+    n_local = args.slots * UNITS_PER_SLOT
+    n_global = n_local * world
+    rx, pil = make_step_inputs(args.slots, 1234 + 1000 * rank, dev)
+    out = torch.empty((n_local, 12 * N_PRB, N_SYM, LAYERS), dtype=torch.complex64, device=dev)
+    sc = torch.empty((n_local, 6), dtype=torch.float64, device=dev)
+
+    launches = 0
+
+    def step():
+        nonlocal launches
+        plan.estimate(rx, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        launches += _lib.lib.srsce_last_launch_count()
+        if world > 1:
+            return sharding.gather_scalars(sc, n_global, RX_ANT)
+        return sc
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    time.sleep(0.02)
+    launches = 0
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(args.steps):
+        k0[k].record()
+        plan.estimate(rx, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        k1[k].record()
+        launches += _lib.lib.srsce_last_launch_count()
+        if world > 1:
+            sharding.gather_scalars(sc, n_global, RX_ANT)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / args.steps
+    if world > 1:
+        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0]), float(t[1])
+    assert bool(torch.isfinite(sc[:, :4]).all()), "non-finite scalars"
+
+    # ---- end to end through the host-buffer entry point
+    e2e_slots = min(args.e2e_slots, args.slots)
+    n_e2e = e2e_slots * UNITS_PER_SLOT
+    h_rx = rx[:n_e2e].cpu().pin_memory()
+    h_pil = pil[:n_e2e // RX_ANT].cpu().pin_memory()
+    h_out = torch.empty((n_e2e, 12 * N_PRB, N_SYM, LAYERS), dtype=torch.complex64).pin_memory()
+    h_sc = torch.empty((n_e2e, 6), dtype=torch.float64).pin_memory()
+    pipe = HostPipeline(plan, 128, RX_ANT, dev)
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        pipe.run(h_rx, h_pil, 1.0, h_out, h_sc)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run(h_rx, h_pil, 1.0, h_out, h_sc)          # returns after every copy has landed in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_ok = bool(torch.equal(h_sc[:64], sc[:64].cpu())) and bool(torch.equal(h_out[:8], out[:8].cpu()))
+
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, burst)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bpu = algorithmic_bytes_per_unit()
+        achieved = bpu * n_local / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        prof = ROOT / "profiles" / "traffic.json"
+        if prof.exists():
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch_at_bench_size")
+        line = {
+            "metric": METRIC, "value": LAYERS * n_global * args.steps / (total_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "complex64 (f32) data, f64 scalars", "data": "synthetic",
+            "config": workload_config(args.slots, e2e_slots),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "estimate_kernel<2,false,false>", "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_unit": bpu, "units_per_launch": n_local, "peak_source": peak_src},
+            "e2e": {"value": LAYERS * n_e2e * world * e2e_steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+                    "steps": e2e_steps, "units_per_step": n_e2e, "matches_device_path": e2e_ok},
+            "gpu_launches": launches, "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--slots", type=int, default=64, help="slots (x256 units) per step and per GPU")
+    ap.add_argument("--e2e-slots", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,11 +14,14 @@
 namespace srsce {
 
 constexpr int kNRE = 12;              // resource elements per PRB
-constexpr int kThreads = 256;         // CTA size of the fused kernel
+constexpr int kThreads = 256;         // estimator threads of a CTA (phase A: pilots -> smoothed channel + scalars)
 constexpr int kWarps = kThreads / 32;
+constexpr int kWarpsB = 4;            // writer warps of a CTA (phase B: interpolate + stream the dense grid out)
+constexpr int kCtaThreads = kThreads + 32 * kWarpsB;
+constexpr int kMinCtasPerSm = 2;      // register budget target (launch bounds) of the fused kernel
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
-constexpr int kMiscBytes = 6144;      // shared-memory slot of the kernel's small tables / reduction scratch
+constexpr int kMiscBytes = 8192;      // shared-memory slot of the kernel's small tables / reduction scratch
 
 // One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
 // a subcarrier at position p of PRB q takes pilots q*R+jl and q*R+jr of its CDM group
@@ -62,7 +65,7 @@ struct PlanDev {
   int32_t cols;            // row_elems / vec store slots per row
   int32_t blend;           // CNN blend of the smoothed pilots active (ce_dl_cnn.py:712-717)
   // shared-memory carve-up (byte offsets from the dynamic smem base)
-  int32_t off_h, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
+  int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
   float cnn_alpha;
   float pad_f;
   double scs_hz;

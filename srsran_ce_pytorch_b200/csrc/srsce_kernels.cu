@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -63,6 +64,13 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
+// Named barriers: 0 is __syncthreads (whole CTA); 1 joins the estimator warps only; 2 ("full") hands
+// hall + the store-slot table from the estimator warps to the writer warps, 3 ("empty") hands them back.
+constexpr int kBarA = 1, kBarFull = 2, kBarEmpty = 3;
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void sync_a() { bar_sync(kBarA, kThreads); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -78,14 +86,14 @@ __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
     const double s = warp_sum(v[k]);
     if (lane == 0) m.red[warp][k] = s;
   }
-  __syncthreads();
+  sync_a();
   if (threadIdx.x < K) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += m.red[w][threadIdx.x];
     m.tot[threadIdx.x] = s;
   }
-  __syncthreads();
+  sync_a();
 }
 
 // Subcarrier of pilot i of CDM group g inside a hop band.
@@ -180,7 +188,7 @@ __device__ void fft_dif_inverse(float2* s, int nl, int M, int log2M, const float
       p[2 * q] = cmul(csub(t0, t2), w2);
       p[3 * q] = cmul(csub(t1, t3), w3);
     }
-    __syncthreads();
+    sync_a();
     n = q;
     log2n = log2q;
   }
@@ -191,26 +199,52 @@ __device__ void fft_dif_inverse(float2* s, int nl, int M, int log2M, const float
       p[0] = cadd(a0, a1);
       p[1] = csub(a0, a1);
     }
-    __syncthreads();
+    sync_a();
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Warp-specialised, software-pipelined CTA.  Per unit:
+//   loader   (estimator threads, one unit ahead)  cp.async gather of the pilot REs of the received grid
+//            into ystage[next]; the pilots themselves are warmed in L2
+//   estimator warps (256 threads)                 phase A out of shared memory -> hall + store-slot table
+//   writer warps (128 threads)                    phase B: interpolate + stream the dense grid to HBM
+// so that the store stream of unit k overlaps the arithmetic of unit k+1 and the loads of unit k+2.
+// Shared-memory layouts (all complex64, layer major so that every per-layer pass is unit stride):
+//   ystage[2][G*N*S_total]     received pilot REs, [hop][group][pilot][symbol], double buffered
+//   hall[hop][layer][N]        smoothed pilots of each hop: written by the FIR, read by the writer warps
+//   ext[layer][EF]             raw pilots with nv virtual pilots and `pad` zeros either side (FIR input),
+//                              EF = N + 2*nv + 2*pad; later the FFT scratch
+//   tiles[writer warp][hop][32][L]  interpolated rows being streamed out
 template <int VEC, bool TWO_HOPS, bool HAS_ROT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kCtaThreads, kMinCtasPerSm)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
-                float2* __restrict__ out, double* __restrict__ scalars, long long n_units) {
+                float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg) {
   extern __shared__ __align__(16) unsigned char smem[];
   float2* const hall = reinterpret_cast<float2*>(smem + P.off_h);
+  float2* const ystage = reinterpret_cast<float2*>(smem + P.off_y);
+  float2* const tiles = reinterpret_cast<float2*>(smem + P.off_tile);
   float2* const ext = reinterpret_cast<float2*>(smem + P.off_ext);
   Misc& m = *reinterpret_cast<Misc*>(smem + P.off_misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = P.n_layers, G = P.n_cdm, R = P.re_per_prb, N = P.n_re, ST = P.n_dmrs_total;
-  const int nv = P.n_virtual, K = P.n_taps;
+  const int nv = P.n_virtual, K = P.n_taps, pad = K >> 1;
+  const int EF = N + 2 * nv + 2 * pad;
   const int n_hops = TWO_HOPS ? 2 : 1;
   const float beta = float(beta_d);
   const float inv_beta = 1.0f / beta;
+  const int n_sc = P.n_sc, row_elems = P.row_elems, cols = P.cols;
+  const int ylen = G * N * ST;
+  const bool filt = P.smoothing == SRSCE_SMOOTH_FILTER;
 
   // plan tables that are indexed per lane go to shared memory once per CTA
   for (int k = tid; k < SRSCE_MAX_TAPS; k += kThreads) m.taps[k] = P.taps[k];
@@ -220,30 +254,75 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   }
   __syncthreads();
 
-  for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-    const float2* __restrict__ rxu = rx + u * su;
-    const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
-    if (tid < 8) m.acc[tid] = 0.0;
-    // (visibility of m.acc is ordered by the barriers inside block_sum below)
-
-    // ===================================== phase A ==========================================
+  if (tid < kThreads) {
+  // ================================ estimator warps ==========================================
+  // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
+  auto stage_unit = [&](long long un, float2* dst) {
+    if (un >= n_units) return;
+    const float2* rxn = rx + un * su;
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
-      const int S = H.n_dmrs, col0 = H.pilot_col0, sc0 = H.band_sc0;
-      float2* const hbuf = hall + hh * N * L;
+      float2* const d0 = dst + G * N * H.pilot_col0;
+      for (int k = tid; k < G * N; k += kThreads) {
+        const int g = (k >= N) ? 1 : 0, i = k - g * N;
+        const float2* src = rxn + (long long)pilot_sc(m, H.band_sc0, R, g, i) * ssc;
+        for (int s = 0; s < H.n_dmrs; ++s) cp_async8(d0 + k * H.n_dmrs + s, src + (long long)H.sym_idx[s] * ssym);
+      }
+    }
+    const char* pn = reinterpret_cast<const char*>(pilots + (un / pilot_share) * ((long long)N * ST * L));
+    const int pil_lines = (N * ST * L * 8 + 127) >> 7;
+    for (int k = tid; k < pil_lines; k += kThreads) prefetch_l2(pn + ((long long)k << 7));
+  };
+  // store-slot table of the writer warps: layer / allocation flags / final CFO rotation of every slot
+  auto build_store_table = [&]() {
+    for (int c = tid; c < cols; c += kThreads) {
+      ColInfo ci;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int el = min(c * VEC + e, row_elems - 1);
+        const int sym = el / L;
+        ci.layer[e] = el - sym * L;
+        int f = (sym >= P.hop[0].start_symbol && sym < P.hop[0].end_symbol) ? 1 : 0;
+        if (TWO_HOPS && sym >= P.hop[1].start_symbol && sym < P.hop[1].end_symbol) f |= 2;
+        ci.flags[e] = f;
+        double sn = 0.0, cs = 1.0;
+        if (HAS_ROT) sincos(2.0 * M_PI * P.t_sym[sym] * m.acc[4], &sn, &cs);   // :922-929
+        ci.rot[e] = make_float2(float(cs), float(sn));
+      }
+      m.col[c] = ci;
+    }
+  };
+  stage_unit(blockIdx.x, ystage);
+  cp_async_commit();
+
+  int it = 0;
+  for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
+    cp_async_wait_all();                                      // this unit's pilot REs have landed ...
+    sync_a();                                                 // ... for every estimator thread
+    const float2* const ys = ystage + (it & 1) * ylen;
+    stage_unit(u + gridDim.x, ystage + ((it + 1) & 1) * ylen);
+    cp_async_commit();
+    if (tid < 8) m.acc[tid] = 0.0;
+    // (visibility of m.acc is ordered by the barriers below)
+
+    // ===================================== phase A ==========================================
+    for (int hh = 0; hh < ((dbg & 1) ? 0 : n_hops); ++hh) {
+      const HopDev& H = P.hop[hh];
+      const int S = H.n_dmrs, col0 = H.pilot_col0;
+      float2* const hbuf = hall + hh * L * N;
+      const float2* const yh = ys + G * N * col0;             // [group][pilot][symbol] of this hop
       const bool est_cfo = S >= 2;
       const bool derot = est_cfo && P.cfo_compensate;
 
       // ---- CFO: correlate the first two pilot symbols (compensate_cfo :357-451)
       if (est_cfo) {
         float2 c[2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};
-        const long long o0 = (long long)H.sym_idx[0] * ssym, o1 = (long long)H.sym_idx[1] * ssym;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < G) {
             for (int i = tid; i < N; i += kThreads) {
-              const long long rs = (long long)pilot_sc(m, sc0, R, g, i) * ssc;
-              const float2 y0 = __ldg(rxu + rs + o0), y1 = __ldg(rxu + rs + o1);
+              const float2 y0 = yh[(g * N + i) * S], y1 = yh[(g * N + i) * S + 1];
               const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -275,18 +354,27 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             m.rot_neg[s] = make_float2(float(cs), float(-sn));
           }
         }
-        __syncthreads();
+        sync_a();
       }
 
       // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584)
       float epre_part = 0.f;
+      if (!filt && hh == 0 && it >= 1) bar_sync(kBarEmpty, kCtaThreads);   // LS writes hall: writers must be done with it
       {
-        float2* const dst = (P.smoothing == SRSCE_SMOOTH_FILTER) ? ext + nv * L : hbuf;
+        float2* const dst = filt ? ext + pad + nv : hbuf;
+        const int dstride = filt ? EF : N;
+        if (filt) {                                  // zero margins of the FIR input
+          for (int k = tid; k < 2 * pad * L; k += kThreads) {
+            const int l = k / (2 * pad), j = k - l * 2 * pad;
+            ext[l * EF + (j < pad ? j : EF - 2 * pad + j)] = make_float2(0.f, 0.f);
+          }
+        }
         const float inv_s = 1.0f / float(S);
         const int n_pairs = (N + 1) >> 1;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < G) {
+            const bool two = 2 * g + 1 < L;
             for (int pr = tid; pr < n_pairs; pr += kThreads) {
               float2 h[2][2];
 #pragma unroll
@@ -294,15 +382,15 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 const int i = 2 * pr + e;
                 float2 a0 = make_float2(0.f, 0.f), a1 = a0;
                 if (i < N) {
-                  const long long rs = (long long)pilot_sc(m, sc0, R, g, i) * ssc;
                   const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
+                  const float2* yp = yh + (g * N + i) * S;
                   for (int s = 0; s < S; ++s) {
-                    const float2 y = __ldg(rxu + rs + (long long)H.sym_idx[s] * ssym);
+                    const float2 y = yp[s];
                     epre_part += y.x * y.x + y.y * y.y;
                     float2 x0 = cmul_conj(y, __ldg(pp + s * L));
                     if (derot) x0 = cmul(x0, m.rot_neg[s]);
                     a0 = cadd(a0, x0);
-                    if (2 * g + 1 < L) {
+                    if (two) {
                       float2 x1 = cmul_conj(y, __ldg(pp + s * L + 1));
                       if (derot) x1 = cmul(x1, m.rot_neg[s]);
                       a1 = cadd(a1, x1);
@@ -321,80 +409,91 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               for (int e = 0; e < 2; ++e) {
                 const int i = i0 + e;
                 if (i < N) {
-                  dst[i * L + 2 * g] = h[e][0];
-                  if (2 * g + 1 < L) dst[i * L + 2 * g + 1] = h[e][1];
+                  dst[2 * g * dstride + i] = h[e][0];
+                  if (two) dst[(2 * g + 1) * dstride + i] = h[e][1];
                 }
               }
             }
           }
         }
       }
-      __syncthreads();
+      sync_a();
 
       // ---- smoothing (:633-668)
       if (P.smoothing == SRSCE_SMOOTH_MEAN) {
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = tid; i < N; i += kThreads)
-          for (int l = 0; l < L; ++l) {
-            const float2 t = hbuf[i * L + l];
-            if (l == 0) { v[0] += t.x; v[1] += t.y; }
-            else if (l == 1) { v[2] += t.x; v[3] += t.y; }
-            else if (l == 2) { v[4] += t.x; v[5] += t.y; }
-            else { v[6] += t.x; v[7] += t.y; }
+#pragma unroll
+        for (int l = 0; l < SRSCE_MAX_LAYERS; ++l) {
+          if (l < L) {
+            float sx = 0.f, sy = 0.f;
+            for (int i = tid; i < N; i += kThreads) {
+              const float2 t = hbuf[l * N + i];
+              sx += t.x;
+              sy += t.y;
+            }
+            v[2 * l] = sx;
+            v[2 * l + 1] = sy;
           }
+        }
         block_sum<8>(m, v);
         const float inv_n = 1.0f / float(N);
         for (int idx = tid; idx < N * L; idx += kThreads) {
-          const int l = idx % L;
+          const int l = idx / N;
           hbuf[idx] = make_float2(float(m.tot[2 * l]) * inv_n, float(m.tot[2 * l + 1]) * inv_n);
         }
-        __syncthreads();
+        sync_a();
       } else if (P.smoothing == SRSCE_SMOOTH_FILTER) {
         if (tid < 2 * L && nv > 0) {
-          const int l = tid >> 1;
+          float2* const x = ext + (tid >> 1) * EF + pad;       // x[0..nv) virtual | x[nv..nv+N) real | virtual
           if ((tid & 1) == 0) {
             virtual_pilots(nv, P.vp_mx, P.vp_den,
-                           [&](int k) { return ext[(nv + k) * L + l]; },
-                           [&](int k, float2 val) { ext[k * L + l] = val; });
+                           [&](int k) { return x[nv + k]; },
+                           [&](int k, float2 val) { x[k] = val; });
           } else {
             virtual_pilots(nv, P.vp_mx, P.vp_den,
-                           [&](int k) { return ext[(nv + N - 1 - k) * L + l]; },
-                           [&](int k, float2 val) { ext[(nv + N + (nv - 1 - k)) * L + l] = val; });
+                           [&](int k) { return x[nv + N - 1 - k]; },
+                           [&](int k, float2 val) { x[nv + N + (nv - 1 - k)] = val; });
           }
         }
-        __syncthreads();
+        sync_a();
+        if (hh == 0 && it >= 1) bar_sync(kBarEmpty, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
         // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493)
-        const int pad = K >> 1, E = N + 2 * nv;
         for (int idx = tid; idx < N * L; idx += kThreads) {
-          const int i = idx / L, l = idx - i * L;
+          const int l = idx / N, i = idx - l * N;
+          const float2* x = ext + l * EF + i + nv + 2 * pad;   // tap k multiplies x[-k]
           double ar = 0.0, ai = 0.0;
           for (int k = 0; k < K; ++k) {
-            const int q = i + nv + pad - k;
-            if (q >= 0 && q < E) {
-              const float2 t = ext[q * L + l];
-              const double w = m.taps[k];
-              ar += w * double(t.x);
-              ai += w * double(t.y);
-            }
+            const float2 t = x[-k];
+            const double w = m.taps[k];
+            ar += w * double(t.x);
+            ai += w * double(t.y);
           }
           hbuf[idx] = make_float2(float(ar), float(ai));
         }
-        __syncthreads();
+        sync_a();
         if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
           for (int idx = tid; idx < N * L; idx += kThreads) {
-            const int i = idx / L, l = idx - i * L;
+            const int l = idx / N, i = idx - l * N;
             const int il = (i == 0) ? 1 : i - 1, ir = (i == N - 1) ? N - 2 : i + 1;
-            const float2 a = hbuf[il * L + l], b = hbuf[idx], c = hbuf[ir * L + l];
+            const float2 a = hbuf[l * N + il], b = hbuf[idx], c = hbuf[l * N + ir];
             ext[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
                                    float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
           }
-          __syncthreads();
+          sync_a();
           for (int idx = tid; idx < N * L; idx += kThreads) {
             const float2 s0 = hbuf[idx], lp = ext[idx];
             hbuf[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
           }
-          __syncthreads();
+          sync_a();
         }
+      }
+
+      // ---- the smoothed pilots of every hop are final: build the store-slot table (final CFO
+      //      rotation :922-929, allocation flags) and release the writer warps; the time alignment
+      //      and noise estimates below only read hall, concurrently with them
+      if (hh == n_hops - 1) {
+        build_store_table();
+        bar_arrive(kBarFull, kCtaThreads);
       }
 
       // ---- time alignment (:674-698)
@@ -406,18 +505,18 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           if (P.fft_regular) {
             for (int idx = tid; idx < nl * M; idx += kThreads) {
               const int l = idx >> log2M, n = idx & (M - 1);
-              ext[idx] = (n < N) ? hbuf[n * L + lb + l] : make_float2(0.f, 0.f);
+              ext[idx] = (n < N) ? hbuf[(lb + l) * N + n] : make_float2(0.f, 0.f);
             }
           } else {
             for (int idx = tid; idx < nl * M; idx += kThreads) ext[idx] = make_float2(0.f, 0.f);
-            __syncthreads();
+            sync_a();
             for (int idx = tid; idx < nl * N; idx += kThreads) {
               const int l = idx / N, i = idx - l * N;
               const int q = i / R;
-              ext[l * M + q * kNRE + posl[i - q * R] - posl[0]] = hbuf[i * L + lb + l];
+              ext[l * M + q * kNRE + posl[i - q * R] - posl[0]] = hbuf[(lb + l) * N + i];
             }
           }
-          __syncthreads();
+          sync_a();
           fft_dif_inverse(ext, nl, M, log2M, P.twiddle);
           for (int t = tid; t < 2 * SRSCE_TA_WINDOW; t += kThreads) {
             const int bin = (t < SRSCE_TA_WINDOW) ? t : SRSCE_TA_FFT - 2 * SRSCE_TA_WINDOW + t;
@@ -429,7 +528,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
             m.prof[t] = acc;
           }
-          __syncthreads();
+          sync_a();
         }
         if (warp == 0) {
           // first maximum of each window; ties keep the lower index, as torch.max / np.argmax
@@ -460,15 +559,16 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < G) {
+            const bool two = 2 * g + 1 < L;
             for (int i = tid; i < N; i += kThreads) {
-              const long long rs = (long long)pilot_sc(m, sc0, R, g, i) * ssc;
               const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
-              const float2 h0 = hbuf[i * L + 2 * g];
-              const float2 h1 = (2 * g + 1 < L) ? hbuf[i * L + 2 * g + 1] : make_float2(0.f, 0.f);
+              const float2* yp = yh + (g * N + i) * S;
+              const float2 h0 = hbuf[2 * g * N + i];
+              const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
               for (int s = 0; s < S; ++s) {
-                const float2 y = __ldg(rxu + rs + (long long)H.sym_idx[s] * ssym);
+                const float2 y = yp[s];
                 float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, m.rot_pos[s]) : h0);
-                if (2 * g + 1 < L) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, m.rot_pos[s]) : h1));
+                if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, m.rot_pos[s]) : h1));
                 const float2 d = csub(y, cscale(e, beta));
                 noise_part += d.x * d.x + d.y * d.y;
               }
@@ -487,10 +587,15 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           m.acc[2] += beta_d * beta_d * double(float(m.tot[2])) * double(S);
         }
       }
-      __syncthreads();
+      sync_a();
     }  // hops
 
-    // ---- per-unit scalars (:899-919, :932-937) and the store-slot table of phase B
+    if (dbg & 1) {                                            // profiling ablation: writers run on stale pilots
+      if (it >= 1) bar_sync(kBarEmpty, kCtaThreads);
+      build_store_table();
+      bar_arrive(kBarFull, kCtaThreads);
+    }
+    // ---- per-unit scalars (:899-919, :932-937)
     if (tid == 0) {
       double* o = scalars + u * 6;
       o[0] = m.acc[1] * P.norm_noise;
@@ -500,49 +605,46 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       o[4] = (m.acc[5] != 0.0) ? m.acc[4] * P.scs_hz : 0.0;
       o[5] = m.acc[5];
     }
-    for (int c = tid; c < P.cols; c += kThreads) {
-      ColInfo ci;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int el = min(c * VEC + e, P.row_elems - 1);
-        const int sym = el / L;
-        ci.layer[e] = el - sym * L;
-        int f = (sym >= P.hop[0].start_symbol && sym < P.hop[0].end_symbol) ? 1 : 0;
-        if (TWO_HOPS && sym >= P.hop[1].start_symbol && sym < P.hop[1].end_symbol) f |= 2;
-        ci.flags[e] = f;
-        double sn = 0.0, cs = 1.0;
-        if (HAS_ROT) sincos(2.0 * M_PI * P.t_sym[sym] * m.acc[4], &sn, &cs);   // :922-929
-        ci.rot[e] = make_float2(float(cs), float(sn));
-      }
-      m.col[c] = ci;
-    }
-    __syncthreads();
-
+    // (the barrier at the top of the next unit orders these reads of m.acc before it is cleared)
+  }
+  } else {
+  // ================================== writer warps ============================================
+  const int wb = warp - kWarps;
+  const long long n_iter = (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  int it = 0;
+  for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    const ColInfo* const colb = m.col;
+    bar_sync(kBarFull, kCtaThreads);
     // ===================================== phase B ==========================================
-    // Each warp takes 32 consecutive subcarriers: lane r interpolates row r into the warp's tile,
-    // then the warp streams the rows out, every lane owning a fixed store slot (symbol, layers).
+    // Each warp takes 32 consecutive subcarriers: lane r interpolates row r into the warp's tile
+    // ([hop][row][layer]), then the warp streams the rows out, every lane owning a fixed store
+    // slot (symbol, layers) of the row.
     {
-      float2* const tile0 = ext + warp * (kTileRows * L * n_hops);
-      float2* const outu = out + u * ((long long)P.n_sc * P.row_elems);
-      const int cols = P.cols;
+      float2* const tile0 = tiles + wb * (kTileRows * L * n_hops);
+      float2* const outu = out + u * ((long long)n_sc * row_elems);
       const bool fast = cols <= 32;
       const int rpi = fast ? 32 / cols : 1;
       const int my_rs = fast ? lane / cols : 0;
       const int my_c = fast ? lane - my_rs * cols : 0;
-      const bool lane_on = fast ? (my_rs < rpi) : true;
-      ColInfo mine = m.col[my_c];
+      const bool lane_on = fast && (my_rs < rpi);
+      const ColInfo mine = colb[my_c];
+      const bool pair = (VEC == 2) && ((L & 1) == 0);      // both elements of a slot are adjacent layers of one symbol
 
-      for (int row0 = warp * kTileRows; row0 < P.n_sc; row0 += kWarps * kTileRows) {
+      for (int row0 = wb * kTileRows; row0 < ((dbg & 2) ? 0 : n_sc); row0 += kWarpsB * kTileRows) {
         const int row = row0 + lane;
-        unsigned in2 = 0;
+        const int rows_here = min(kTileRows, n_sc - row0);
+        unsigned in1 = 0, in2 = 0;
         __syncwarp();
 #pragma unroll
         for (int hh = 0; hh < n_hops; ++hh) {
           const HopDev& H = P.hop[hh];
-          float2* const hb = hall + hh * N * L;
+          const float2* const hb = hall + hh * L * N;
           float2* const trow = tile0 + (hh * kTileRows + lane) * L;
           const bool inband = row >= H.band_sc0 && row < H.band_sc1;
-          if (hh == 1) in2 = __ballot_sync(0xffffffffu, inband);
+          const unsigned bal = __ballot_sync(0xffffffffu, inband);
+          if (hh == 0) in1 = bal;
+          else in2 = bal;
+          if (bal == 0) continue;                    // whole tile outside this hop's band
           if (!inband) {
             for (int l = 0; l < L; ++l) trow[l] = make_float2(0.f, 0.f);
           } else {
@@ -553,13 +655,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               if (g < G) {
                 float2 v0, v1 = make_float2(0.f, 0.f);
                 const bool two = 2 * g + 1 < L;
+                const float2* const ha = hb + 2 * g * N;
                 if (P.fill == SRSCE_FILL_LINEAR) {
                   const LerpEntry e = m.lerp[g][pos];
                   const int il = max(0, min(N - 1, q * R + e.jl)), ir = max(0, min(N - 1, q * R + e.jr));
-                  const float2 l0 = hb[il * L + 2 * g], r0 = hb[ir * L + 2 * g];
+                  const float2 l0 = ha[il], r0 = ha[ir];
                   v0 = make_float2(l0.x + e.alpha * (r0.x - l0.x), l0.y + e.alpha * (r0.y - l0.y));
                   if (two) {
-                    const float2 l1 = hb[il * L + 2 * g + 1], r1 = hb[ir * L + 2 * g + 1];
+                    const float2 l1 = ha[N + il], r1 = ha[N + ir];
                     v1 = make_float2(l1.x + e.alpha * (r1.x - l1.x), l1.y + e.alpha * (r1.y - l1.y));
                   }
                 } else {
@@ -570,11 +673,11 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                   v0 = make_float2(0.f, 0.f);
                   for (int t = 0; t < T; ++t) {
                     const float w = __ldg(cf + t);
-                    const float2 a = hb[(k0 + t) * L + 2 * g];
+                    const float2 a = ha[k0 + t];
                     v0.x += w * a.x;
                     v0.y += w * a.y;
                     if (two) {
-                      const float2 b = hb[(k0 + t) * L + 2 * g + 1];
+                      const float2 b = ha[N + k0 + t];
                       v1.x += w * b.x;
                       v1.y += w * b.y;
                     }
@@ -588,36 +691,57 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
         __syncwarp();
 
-        const int rows_here = min(kTileRows, P.n_sc - row0);
         if (fast) {
           if (lane_on) {
-            for (int r = my_rs; r < rows_here; r += rpi) {
-              float2 val[2];
-#pragma unroll
-              for (int e = 0; e < VEC; ++e) {
-                float2 t = make_float2(0.f, 0.f);
-                if (TWO_HOPS && (mine.flags[e] & 2) && ((in2 >> r) & 1u)) t = tile0[(kTileRows + r) * L + mine.layer[e]];
-                else if (mine.flags[e] & 1) t = tile0[r * L + mine.layer[e]];
-                val[e] = HAS_ROT ? cmul(t, mine.rot[e]) : t;
+            float2* dst = outu + (long long)(row0 + my_rs) * row_elems + my_c * VEC;
+            const long long dstep = (long long)rpi * row_elems;
+            if ((in1 | in2) == 0) {                  // tile entirely outside every band: zeros
+              for (int r = my_rs; r < rows_here; r += rpi, dst += dstep) {
+                if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(0.f, 0.f, 0.f, 0.f));
+                else __stcs(dst, make_float2(0.f, 0.f));
               }
-              float2* dst = outu + (long long)(row0 + r) * P.row_elems + my_c * VEC;
-              if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(val[0].x, val[0].y, val[1].x, val[1].y));
-              else __stcs(dst, val[0]);
+            } else if (pair && !TWO_HOPS) {
+              // hot loop of the headline configuration: one 16-byte shared load, one 16-byte streaming store
+              const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
+              const int sstep = rpi * L / 2;
+              const bool on = (mine.flags[0] & 1) != 0;
+#pragma unroll 4
+              for (int r = my_rs; r < rows_here; r += rpi, dst += dstep, src += sstep) {
+                float4 v = on ? *src : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_ROT) {
+                  const float2 a = cmul(make_float2(v.x, v.y), mine.rot[0]), b = cmul(make_float2(v.z, v.w), mine.rot[1]);
+                  v = make_float4(a.x, a.y, b.x, b.y);
+                }
+                __stcs(reinterpret_cast<float4*>(dst), v);
+              }
+            } else {
+              for (int r = my_rs; r < rows_here; r += rpi, dst += dstep) {
+                float2 val[2];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                  float2 t = make_float2(0.f, 0.f);
+                  if (TWO_HOPS && (mine.flags[e] & 2) && ((in2 >> r) & 1u)) t = tile0[(kTileRows + r) * L + mine.layer[e]];
+                  else if ((mine.flags[e] & 1) && ((in1 >> r) & 1u)) t = tile0[r * L + mine.layer[e]];
+                  val[e] = HAS_ROT ? cmul(t, mine.rot[e]) : t;
+                }
+                if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(val[0].x, val[0].y, val[1].x, val[1].y));
+                else __stcs(dst, val[0]);
+              }
             }
           }
         } else {
           for (int r = 0; r < rows_here; ++r) {
             for (int c = lane; c < cols; c += 32) {
-              const ColInfo ci = m.col[c];
+              const ColInfo ci = colb[c];
               float2 val[2];
 #pragma unroll
               for (int e = 0; e < VEC; ++e) {
                 float2 t = make_float2(0.f, 0.f);
                 if (TWO_HOPS && (ci.flags[e] & 2) && ((in2 >> r) & 1u)) t = tile0[(kTileRows + r) * L + ci.layer[e]];
-                else if (ci.flags[e] & 1) t = tile0[r * L + ci.layer[e]];
+                else if ((ci.flags[e] & 1) && ((in1 >> r) & 1u)) t = tile0[r * L + ci.layer[e]];
                 val[e] = HAS_ROT ? cmul(t, ci.rot[e]) : t;
               }
-              float2* dst = outu + (long long)(row0 + r) * P.row_elems + c * VEC;
+              float2* dst = outu + (long long)(row0 + r) * row_elems + c * VEC;
               if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(val[0].x, val[0].y, val[1].x, val[1].y));
               else __stcs(dst, val[0]);
             }
@@ -625,12 +749,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
     }
-    __syncthreads();   // tiles alias ext, m.col / m.acc are rewritten by the next unit
+    if (it + 1 < n_iter) bar_arrive(kBarEmpty, kCtaThreads);         // hall / store table may be rewritten
+  }
   }
 }
 
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
-                         double, float2*, double*, long long);
+                         double, float2*, double*, long long, int);
 
 KernelFn pick_kernel(int vec, bool two_hops, bool has_rot) {
   if (vec == 2) {
@@ -639,6 +764,16 @@ KernelFn pick_kernel(int vec, bool two_hops, bool has_rot) {
   }
   if (two_hops) return has_rot ? estimate_kernel<1, true, true> : estimate_kernel<1, true, false>;
   return has_rot ? estimate_kernel<1, false, true> : estimate_kernel<1, false, false>;
+}
+
+// Ablation switch for profiling only (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B);
+// results are garbage when set, so it is read from the environment and never from the API.
+int debug_mode() {
+  static const int mode = [] {
+    const char* e = getenv("SRSCE_DEBUG_ABLATE");
+    return e ? atoi(e) : 0;
+  }();
+  return mode;
 }
 
 std::string cuda_msg(const char* what, cudaError_t e) {
@@ -693,7 +828,7 @@ int upload_plan(Plan& p, std::string& err) {
     return SRSCE_ERR_CUDA;
   }
   int per_sm = 0, sms = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), kThreads, p.dev.smem_bytes)) != cudaSuccess ||
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), kCtaThreads, p.dev.smem_bytes)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
     err = cuda_msg("occupancy query", e);
     return SRSCE_ERR_CUDA;
@@ -724,9 +859,10 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   KernelFn fn = pick_kernel(p.dev.vec, p.dev.n_hops == 2, p.dev.cfo_compensate && p.dev.cfo_defined);
   const long long cap = (long long)p.n_sms * p.ctas_per_sm;
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
-  fn<<<grid, kThreads, p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+  fn<<<grid, kCtaThreads, p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
-      static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units);
+      static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
+      debug_mode());
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = cuda_msg("kernel launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;

@@ -418,18 +418,22 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     v.fill_terms = (d.fill == SRSCE_FILL_CNN) ? terms : 2;
   }
 
-  // shared memory: smoothed pilots of every hop | raw pilots + virtual pilots, later FFT scratch,
-  // later the warps' expansion tiles | small tables and reduction scratch
+  // shared memory: smoothed pilots of every hop | staged pilot REs of this and the next unit |
+  // raw pilots + virtual pilots, later FFT scratch | the writer warps' expansion tiles | small tables
   {
     const int h_elems = n_hops * N * L;
-    int ext = (N + 2 * v.n_virtual) * L;
-    ext = std::max(ext, v.fft_layers * v.fft_size);
-    ext = std::max(ext, kWarps * kTileRows * L * n_hops + kWarps * kTileRows / 2);
+    const int y_elems = 2 * G * N * s_total;
+    int ext = (N + 2 * v.n_virtual + 2 * (v.n_taps / 2)) * L;      // FIR input incl. virtual pilots and zero margins
+    ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
+    ext = std::max(ext, N * L);                                   // scratch of the CNN blend
+    const int tile_elems = kWarpsB * kTileRows * L * n_hops;
+    auto up16 = [](int bytes) { return ((bytes + 15) / 16) * 16; };
     v.ext_elems = ext;
     v.off_h = 0;
-    v.off_ext = v.off_h + ((h_elems * 8 + 15) / 16) * 16;
-    v.off_tile = v.off_ext;
-    v.off_misc = v.off_ext + ((ext * 8 + 15) / 16) * 16;
+    v.off_y = v.off_h + up16(h_elems * 8);
+    v.off_ext = v.off_y + up16(y_elems * 8);
+    v.off_tile = v.off_ext + up16(ext * 8);
+    v.off_misc = v.off_tile + up16(tile_elems * 8);
     v.smem_bytes = v.off_misc + kMiscBytes;
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);

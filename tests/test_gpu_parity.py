@@ -161,3 +161,29 @@ def test_empty_batch_and_return_types():
     one = estimator.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, hop2, cfg)
     assert one[0].shape == (3276, 14, 4) and one[5].shape == (0,) and one[5].dtype == torch.float64
     assert all(t.dim() == 0 and t.dtype == torch.float64 for t in one[1:5])
+
+
+def test_persistent_loop_many_units_per_cta():
+    """More units than resident CTAs: every CTA walks several units through its double-buffered
+    staging / estimator / writer pipeline.  Batch independence must still hold bit for bit."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    for two_hops in (False, True):
+        hop1 = synth.make_hop(24, 2, 8, [1, 3], "comb4", 2)
+        hop2 = synth.make_hop(24, 12, 8, [8, 10], "comb4", 2) if two_hops else synth.no_hop()
+        cfg = synth.make_config(30e3, "filter", True)
+        n = 3000
+        data = synth.make_units(hop1, hop2, cfg, 4, n, pilot_share=4, seed=77, device="cuda")
+        out, sc = estimator.srs_channel_estimator_batched(data["rx"], data["pilots"], 1.0, hop1, hop2, cfg, pilot_share=4)
+        for b0 in (0, 1488, 2992):
+            sub, sc_sub = estimator.srs_channel_estimator_batched(data["rx"][b0:b0 + 8], data["pilots"][b0 // 4:b0 // 4 + 2],
+                                                                  1.0, hop1, hop2, cfg, pilot_share=4)
+            assert torch.equal(sub, out[b0:b0 + 8]) and torch.equal(sc_sub, sc[b0:b0 + 8]), (two_hops, b0)
+        rx, pil = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+        for b in (5, 1777, 2999):
+            diag = {}
+            want = ce_oracle.estimate(rx[b], pil[b // 4], 1.0, hop1, hop2, cfg, diagnostics=diag)
+            mx, nmse = tol.grid_errors(out[b].cpu().numpy(), want[0])
+            assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (two_hops, b, mx, nmse)
+            s = sc[b].cpu().numpy()
+            tol.check_scalars([s[0], s[1], s[2], s[3], s[4] if s[5] else None], want[1:], 30e3, diag["ta_margin"],
+                              tag=f"persistent/{two_hops}/{b}")
