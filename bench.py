@@ -42,6 +42,7 @@ def workload_config(slots, e2e_slots=None):
     cfg = {"workload": "config2: ce_rule_tensorized batched, 273 PRB 30 kHz, 4 ports, 4 rx antennas, comb-4, "
                        "64 UEs per slot, 1 pilot symbol, 14-symbol grid, filter smoothing, CFO compensation on",
            "units_per_step": slots * UNITS_PER_SLOT, "slots_per_step": slots, "estimates_per_unit": LAYERS,
+           "rx_layout": "reference ([n_sc, n_sym] row major per unit, one grid per unit)",
            "l2_policy": "inputs+outputs per step (>= 7 GB) exceed the 126 MB L2; no flush needed"}
     if e2e_slots is not None:
         cfg["e2e_units_per_step"] = e2e_slots * UNITS_PER_SLOT
@@ -72,7 +73,7 @@ def cpu_pool(n_distinct=16):
                                 ce_oracle.HopSpec.absent(), ce_oracle.est_from_any(cfg))
 
 
-def cpu_baseline(units_per_worker=96):
+def cpu_baseline(units_per_worker=480):
     pool = cpu_pool()
     try:
         pool.run(4)
@@ -126,7 +127,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.mask, self.max_mhz, self.stop_flag, self.err = index, [], 0, None, False, None
+        self.index, self.samples, self.max_mhz, self.stop_flag, self.err, self.ready = index, [], None, False, None, False
 
     def run(self):
         try:
@@ -134,19 +135,29 @@ class ClockSampler(threading.Thread):
             nv.nvmlInit()
             h = nv.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.ready = True
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                time.sleep(0.005)
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h))))
+                time.sleep(0.002)
         except Exception as e:  # noqa: BLE001 -- the bench must not die on a monitoring problem
             self.err = repr(e)
+            self.ready = True
 
-    def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
-                "reasons": [n for b, n in self.REASONS.items() if self.mask & b and n != "gpu_idle"],
-                "samples": len(s), **({"error": self.err} if self.err else {})}
+    def summary(self, t0, t1):
+        """Median SM clock and the union of throttle reasons over the samples taken in [t0, t1]
+        (falls back to the nearest samples when the window is shorter than the sampling period)."""
+        win = [x for x in self.samples if t0 <= x[0] <= t1]
+        if not win and self.samples:
+            win = sorted(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]
+        clocks = sorted(x[1] for x in win)
+        mask = 0
+        for x in win:
+            mask |= x[2]
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if mask & b and n != "gpu_idle"],
+                "samples": len(win), **({"error": self.err} if self.err else {})}
 
 
 def physical_gpu_index(local):
@@ -214,17 +225,20 @@ def run_ours(args):
             return sharding.gather_scalars(sc, n_global, RX_ANT)
         return sc
 
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         step()
     torch.cuda.synchronize()
+    for _ in range(200):                       # NVML is up before the timed region starts
+        if sampler.ready:
+            break
+        time.sleep(0.01)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-
-    sampler = ClockSampler(physical_gpu_index(local))
-    sampler.start()
-    time.sleep(0.02)
     launches = 0
+    wall0 = time.perf_counter()
     k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -241,6 +255,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    wall1 = time.perf_counter()
     sampler.stop_flag = True
     sampler.join(timeout=2.0)
 
@@ -251,6 +266,25 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, kern_ms = float(t[0]), float(t[1])
     assert bool(torch.isfinite(sc[:, :4]).all()), "non-finite scalars"
+
+    # ---- the same step with symbol-major grids ([B, n_sym, n_sc] memory viewed as [B, n_sc, n_sym]), the
+    #      layout OFDM front ends produce; the batched entry point takes any strides
+    alt = None
+    if not args.no_alt_layout:
+        rx_sm = rx.transpose(1, 2).contiguous().transpose(1, 2)
+        for _ in range(3):
+            plan.estimate(rx_sm, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(args.steps):
+            plan.estimate(rx_sm, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        a1.record()
+        torch.cuda.synchronize()
+        alt_ms = a0.elapsed_time(a1) / args.steps
+        alt = {"rx_layout": "symbol-major", "value": LAYERS * n_local / (alt_ms * 1e-3), "unit": UNIT,
+               "kernel_ms": alt_ms, "n_gpus": 1}
+        del rx_sm
 
     # ---- end to end through the host-buffer entry point
     e2e_slots = min(args.e2e_slots, args.slots)
@@ -301,8 +335,11 @@ def run_ours(args):
             "e2e": {"value": LAYERS * n_e2e * world * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
                     "steps": e2e_steps, "units_per_step": n_e2e, "matches_device_path": e2e_ok},
-            "gpu_launches": launches, "clocks": sampler.summary(),
+            "gpu_launches": launches, "clocks": sampler.summary(wall0, wall1),
         }
+        if alt is not None:
+            alt["roofline_frac"] = bpu * n_local / (alt["kernel_ms"] * 1e-3) / 1e9 / peak
+            line["alt_layout"] = alt
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -320,6 +357,7 @@ def main():
     ap.add_argument("--e2e-slots", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-layout", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

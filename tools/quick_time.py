@@ -13,6 +13,14 @@ gen = 256
 data = synth.make_units(hop1, synth.no_hop(), cfg, 4, gen, pilot_share=4, seed=1, device="cuda")
 rx = data["rx"].repeat(n_units // gen, 1, 1)
 pil = data["pilots"].repeat(n_units // gen, 1, 1, 1)
+import os, ctypes, glob
+if os.environ.get("L2GRAN"):
+    import nvidia.cuda_runtime as cr
+    rt = ctypes.CDLL(glob.glob(os.path.dirname(cr.__file__) + "/lib/libcudart.so*")[0])
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2GRAN"])))
+    val = ctypes.c_size_t()
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print("cudaLimitMaxL2FetchGranularity rc", rc, "now", val.value)
 plan = estimator.make_plan(273, 14, 4, hop1, synth.no_hop(), cfg)
 out = torch.empty((n_units, 3276, 14, 4), dtype=torch.complex64, device="cuda")
 sc = torch.empty((n_units, 6), dtype=torch.float64, device="cuda")
