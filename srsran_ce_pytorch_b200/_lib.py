@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libsrsce.so"
+LIB_PATH = Path(os.environ.get("SRSCE_LIBRARY", _HERE / "libsrsce.so"))   # override: A/B runs of two builds
 
 MAX_SYMBOLS = 14
 ABI_VERSION = 1

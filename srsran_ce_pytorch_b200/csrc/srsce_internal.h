@@ -14,13 +14,16 @@
 namespace srsce {
 
 constexpr int kNRE = 12;              // resource elements per PRB
-constexpr int kThreads = 256;         // estimator threads of a CTA (phase A: pilots -> smoothed channel + scalars)
-constexpr int kWarps = kThreads / 32;
-constexpr int kWarpsB = 4;            // writer warps of a CTA (phase B: interpolate + stream the dense grid out)
-constexpr int kCtaThreads = kThreads + 32 * kWarpsB;
-constexpr int kMinCtasPerSm = 2;      // register budget target (launch bounds) of the fused kernel
+// A CTA = NA estimator threads (phase A: pilots -> smoothed channel + scalars) + writer warps (phase B:
+// interpolate + stream the dense grid out).  Geometries whose shared-memory footprint allows two CTAs
+// per SM run NA = 256 (+4 writer warps); heavier ones run one CTA of NA = 512 (+8 writer warps).
+constexpr int kMaxWarpsA = 16;
+constexpr int kMaxWarpsB = 8;
+constexpr int writer_warps(int na) { return na == 256 ? 4 : 8; }
+constexpr int cta_threads(int na) { return na + 32 * writer_warps(na); }
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
+constexpr int kCnnEdgeRows = 2 * kNRE; // band rows at either end whose CNN operator rows are looked up individually
 constexpr int kMiscBytes = 8192;      // shared-memory slot of the kernel's small tables / reduction scratch
 
 // One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
@@ -60,10 +63,12 @@ struct PlanDev {
   int32_t fft_regular;     // 1: M-point transform of the pilot vector (comb stride divides 4096); 0: zero-stuffed 4096
   int32_t fft_layers;      // layers transformed together in the scratch buffer
   int32_t fill_terms;      // T of the CNN operator
+  int32_t fill_periodic;   // interior rows of the CNN operator repeat with the PRB period: use cnn_coef / cnn_idx0
   int32_t row_elems;       // n_sym * n_layers complex64 per subcarrier row of the output
   int32_t vec;             // 2: float4 stores (row_elems even), 1: float2 stores
   int32_t cols;            // row_elems / vec store slots per row
   int32_t blend;           // CNN blend of the smoothed pilots active (ce_dl_cnn.py:712-717)
+  int32_t est_threads;     // NA: 256 (two CTAs per SM) or 512 (one CTA per SM)
   // shared-memory carve-up (byte offsets from the dynamic smem base)
   int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
   float cnn_alpha;
@@ -75,9 +80,11 @@ struct PlanDev {
   double norm_rsrp, norm_epre, norm_noise, ta_scale, ta_hop_div;  // :899-919
   int32_t re_pos[2][kNRE];                // positions of the set bits of each CDM group's RE mask
   LerpEntry lerp[2][kNRE];
+  float cnn_coef[2][kNRE][kMaxFillTerms];   // CNN operator of an interior PRB: row pos takes pilots cnn_idx0 + q*R + t
+  int32_t cnn_idx0[2][kNRE];
   HopDev hop[2];
   // device tables (owned by the plan)
-  const float2* twiddle;                  // exp(+j*2*pi*k/4096), k < 4096
+  const float2* twiddle;                  // exp(+j*2*pi*k/M), k < M = fft_size
   const int32_t* fill_idx;                // [n_cdm][band rows]           (CNN fill only)
   const float* fill_coef;                 // [n_cdm][band rows][fill_terms]
 };

@@ -41,7 +41,7 @@ struct ColInfo {           // one store slot of an output row (VEC consecutive c
 };
 
 struct Misc {
-  double red[kWarps][8];
+  double red[kMaxWarpsA][8];
   double tot[8];
   double acc[8];           // 0 epre, 1 noise, 2 rsrp, 3 ta, 4 cfo, 5 cfo defined
   double taps[SRSCE_MAX_TAPS + 1];
@@ -50,6 +50,10 @@ struct Misc {
   float prof[2 * SRSCE_TA_WINDOW];
   LerpEntry lerp[2][kNRE];
   int32_t re_pos[2][kNRE];
+  float cnn_coef[2][kNRE][kMaxFillTerms];
+  int32_t cnn_idx0[2][kNRE];
+  float vp_mod[SRSCE_MAX_LAYERS][2][12];   // modulus / phase of the edge pilots (virtual-pilot regression)
+  float vp_ph[SRSCE_MAX_LAYERS][2][12];
   ColInfo col[SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
@@ -69,7 +73,8 @@ __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2
 constexpr int kBarA = 1, kBarFull = 2, kBarEmpty = 3;
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void sync_a() { bar_sync(kBarA, kThreads); }
+template <int NA>
+__device__ __forceinline__ void sync_a() { bar_sync(kBarA, NA); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -78,7 +83,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Sum K per-thread values over the CTA; every thread gets the totals in m.tot[0..K).
-template <int K>
+template <int NA, int K>
 __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -86,14 +91,14 @@ __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
     const double s = warp_sum(v[k]);
     if (lane == 0) m.red[warp][k] = s;
   }
-  sync_a();
+  sync_a<NA>();
   if (threadIdx.x < K) {
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += m.red[w][threadIdx.x];
+    for (int w = 0; w < NA / 32; ++w) s += m.red[w][threadIdx.x];
     m.tot[threadIdx.x] = s;
   }
-  sync_a();
+  sync_a<NA>();
 }
 
 // Subcarrier of pilot i of CDM group g inside a hop band.
@@ -102,54 +107,43 @@ __device__ __forceinline__ int pilot_sc(const Misc& m, int band_sc0, int R, int 
   return band_sc0 + q * kNRE + m.re_pos[g][i - q * R];
 }
 
-// create_virtual_pilots (:69-140) for one edge of one layer.  edge(k) is the k-th pilot counted
-// from the band edge inwards; out(k), k = 0..nv-1, receives the virtual pilot at abscissa k - nv.
-template <typename EdgeFn, typename OutFn>
-__device__ void virtual_pilots(int nv, double mx, double den, EdgeFn edge, OutFn out) {
-  if (nv <= 0) return;
+// create_virtual_pilots (:69-140), second half: given modulus and (float32) phase of the nv pilots at one
+// edge of one layer (k counted from the band edge inwards), return the virtual pilot at abscissa k_out - nv.
+// Straight-line fits of modulus and unwrapped phase in float64 (:105-138); unwrap as _unwrap_1d (:35-66).
+__device__ float2 virtual_pilot(int nv, double mx, double den, const float* mod, const float* ph, int k_out) {
   if (nv == 1) {                                    // :95-101 constant extrapolation
-    const float2 e = edge(0);
-    const float amp = sqrtf(e.x * e.x + e.y * e.y);
-    const float ph = atan2f(e.y, e.x);
     float s, c;
-    sincosf(ph, &s, &c);
-    out(0, make_float2(amp * c, amp * s));
-    return;
+    sincosf(ph[0], &s, &c);
+    return make_float2(mod[0] * c, mod[0] * s);
   }
-  // straight-line fits of modulus and unwrapped phase, float64 (:105-138); unwrap as _unwrap_1d (:35-66)
-  double sy_m = 0.0, sxy_m = 0.0, sy_p = 0.0, sxy_p = 0.0;
-  double prev = 0.0, corr = 0.0;
+  double sy_m = 0.0, sxy_m = 0.0, sy_p = 0.0, sxy_p = 0.0, prev = 0.0, corr = 0.0;
   const double two_pi = 2.0 * M_PI;
   for (int k = 0; k < nv; ++k) {
-    const float2 e = edge(k);
-    const double mod = double(sqrtf(e.x * e.x + e.y * e.y));
-    const double ph = double(atan2f(e.y, e.x));
+    const double a = double(mod[k]), p = double(ph[k]);
     if (k > 0) {
-      const double d = ph - prev;
-      double dm = fmod(d + M_PI, two_pi);
-      if (dm < 0.0) dm += two_pi;                   // floored modulo, as torch.remainder
-      dm -= M_PI;
-      if (dm == -M_PI && d > 0.0) dm += two_pi;
-      if (fabs(d) >= M_PI) corr += dm - d;
+      const double d = p - prev;
+      if (fabs(d) >= M_PI) {
+        double dm = (d + M_PI) - two_pi * floor((d + M_PI) / two_pi) - M_PI;   // floored modulo, as torch.remainder
+        if (dm == -M_PI && d > 0.0) dm += two_pi;
+        corr += dm - d;
+      }
     }
-    prev = ph;
-    const double phu = ph + corr;
-    sy_m += mod;
-    sxy_m += double(k) * mod;
-    sy_p += phu;
-    sxy_p += double(k) * phu;
+    prev = p;
+    const double pu = p + corr;
+    sy_m += a;
+    sxy_m += double(k) * a;
+    sy_p += pu;
+    sxy_p += double(k) * pu;
   }
   const double n = double(nv);
   const double my_m = sy_m / n, my_p = sy_p / n;
   const double a_m = (sxy_m - n * mx * my_m) / den, b_m = my_m - a_m * mx;
   const double a_p = (sxy_p - n * mx * my_p) / den, b_p = my_p - a_p * mx;
-  for (int k = 0; k < nv; ++k) {
-    const double x = double(k - nv);
-    const double mod = a_m * x + b_m, arg = a_p * x + b_p;
-    double s, c;
-    sincos(arg, &s, &c);
-    out(k, make_float2(float(mod * c), float(mod * s)));
-  }
+  const double x = double(k_out - nv);
+  double sn, cs;
+  sincos(a_p * x + b_p, &sn, &cs);
+  const double amp = a_m * x + b_m;
+  return make_float2(float(amp * cs), float(amp * sn));
 }
 
 // Where output bin k of the in-place decimation-in-frequency transform of length M ends up.
@@ -167,14 +161,15 @@ __device__ __forceinline__ int dif_position(int k, int M) {
 
 // In-place inverse (e^{+j...}) DIF FFT of `nl` length-M vectors stored back to back in s[]:
 // radix-4 passes, one radix-2 pass if M is an odd power of two.  Output in digit-reversed order.
+template <int NA>
 __device__ void fft_dif_inverse(float2* s, int nl, int M, int log2M, const float2* __restrict__ tw) {
   const int tid = threadIdx.x;
   int n = M, log2n = log2M;
   while (n >= 4) {
     const int q = n >> 2, log2q = log2n - 2;
-    const int step = SRSCE_TA_FFT >> log2n;         // twiddle stride: w_n^j = tw[j * 4096 / n]
+    const int step = M >> log2n;                    // twiddle stride: w_n^j = tw[j * M / n], tw[k] = exp(+j 2 pi k / M)
     const int per_vec = M >> 2;
-    for (int b = tid; b < nl * per_vec; b += kThreads) {
+    for (int b = tid; b < nl * per_vec; b += NA) {
       const int l = b / per_vec, r = b - l * per_vec;
       const int blk = r >> log2q, j = r & (q - 1);
       float2* p = s + l * M + (blk << log2n) + j;
@@ -188,18 +183,18 @@ __device__ void fft_dif_inverse(float2* s, int nl, int M, int log2M, const float
       p[2 * q] = cmul(csub(t0, t2), w2);
       p[3 * q] = cmul(csub(t1, t3), w3);
     }
-    sync_a();
+    sync_a<NA>();
     n = q;
     log2n = log2q;
   }
   if (n == 2) {
-    for (int b = tid; b < nl * (M >> 1); b += kThreads) {
+    for (int b = tid; b < nl * (M >> 1); b += NA) {
       float2* p = s + 2 * b;
       const float2 a0 = p[0], a1 = p[1];
       p[0] = cadd(a0, a1);
       p[1] = csub(a0, a1);
     }
-    sync_a();
+    sync_a<NA>();
   }
 }
 
@@ -223,11 +218,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   ext[layer][EF]             raw pilots with nv virtual pilots and `pad` zeros either side (FIR input),
 //                              EF = N + 2*nv + 2*pad; later the FFT scratch
 //   tiles[writer warp][hop][32][L]  interpolated rows being streamed out
-template <int VEC, bool TWO_HOPS, bool HAS_ROT>
-__global__ void __launch_bounds__(kCtaThreads, kMinCtasPerSm)
+template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT>
+__global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 4 : 8), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg) {
+  constexpr int kThreads = NA;                              // estimator threads
+  constexpr int kWarpsB = (NA == 256) ? 4 : 8;            // = writer_warps(NA)
+  constexpr int kCtaThreads = NA + 32 * kWarpsB;
   extern __shared__ __align__(16) unsigned char smem[];
   float2* const hall = reinterpret_cast<float2*>(smem + P.off_h);
   float2* const ystage = reinterpret_cast<float2*>(smem + P.off_y);
@@ -251,7 +249,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   for (int k = tid; k < 2 * kNRE; k += kThreads) {
     m.lerp[k / kNRE][k % kNRE] = P.lerp[k / kNRE][k % kNRE];
     m.re_pos[k / kNRE][k % kNRE] = P.re_pos[k / kNRE][k % kNRE];
+    m.cnn_idx0[k / kNRE][k % kNRE] = P.cnn_idx0[k / kNRE][k % kNRE];
   }
+  for (int k = tid; k < 2 * kNRE * kMaxFillTerms; k += kThreads)
+    (&m.cnn_coef[0][0][0])[k] = (&P.cnn_coef[0][0][0])[k];
   __syncthreads();
 
   if (tid < kThreads) {
@@ -299,7 +300,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
     const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
-    sync_a();                                                 // ... for every estimator thread
+    sync_a<NA>();                                                 // ... for every estimator thread
     const float2* const ys = ystage + (it & 1) * ylen;
     stage_unit(u + gridDim.x, ystage + ((it + 1) & 1) * ylen);
     cp_async_commit();
@@ -335,7 +336,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
         }
         double v[8] = {c[0][0].x, c[0][0].y, c[0][1].x, c[0][1].y, c[1][0].x, c[1][0].y, c[1][1].x, c[1][1].y};
-        block_sum<8>(m, v);
+        block_sum<NA, 8>(m, v);
         if (tid == 0) {
           double tot = 0.0;
           for (int k = 0; k + 1 < L; k += 2) {
@@ -354,7 +355,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             m.rot_neg[s] = make_float2(float(cs), float(-sn));
           }
         }
-        sync_a();
+        sync_a<NA>();
       }
 
       // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584)
@@ -417,7 +418,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
         }
       }
-      sync_a();
+      sync_a<NA>();
 
       // ---- smoothing (:633-668)
       if (P.smoothing == SRSCE_SMOOTH_MEAN) {
@@ -435,27 +436,32 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             v[2 * l + 1] = sy;
           }
         }
-        block_sum<8>(m, v);
+        block_sum<NA, 8>(m, v);
         const float inv_n = 1.0f / float(N);
         for (int idx = tid; idx < N * L; idx += kThreads) {
           const int l = idx / N;
           hbuf[idx] = make_float2(float(m.tot[2 * l]) * inv_n, float(m.tot[2 * l + 1]) * inv_n);
         }
-        sync_a();
+        sync_a<NA>();
       } else if (P.smoothing == SRSCE_SMOOTH_FILTER) {
-        if (tid < 2 * L && nv > 0) {
-          float2* const x = ext + (tid >> 1) * EF + pad;       // x[0..nv) virtual | x[nv..nv+N) real | virtual
-          if ((tid & 1) == 0) {
-            virtual_pilots(nv, P.vp_mx, P.vp_den,
-                           [&](int k) { return x[nv + k]; },
-                           [&](int k, float2 val) { x[k] = val; });
-          } else {
-            virtual_pilots(nv, P.vp_mx, P.vp_den,
-                           [&](int k) { return x[nv + N - 1 - k]; },
-                           [&](int k, float2 val) { x[nv + N + (nv - 1 - k)] = val; });
+        if (nv > 0) {
+          // one thread per (layer, edge, pilot): modulus / phase first, then every thread fits the two
+          // lines of its edge and evaluates its own virtual pilot
+          const int l = tid / (2 * nv), r = tid - l * 2 * nv, end = r / nv, k = r - end * nv;
+          float2* const x = ext + l * EF + pad;              // x[0..nv) virtual | x[nv..nv+N) real | virtual
+          if (tid < 2 * L * nv) {
+            const float2 e = end ? x[nv + N - 1 - k] : x[nv + k];
+            m.vp_mod[l][end][k] = sqrtf(e.x * e.x + e.y * e.y);
+            m.vp_ph[l][end][k] = atan2f(e.y, e.x);
+          }
+          sync_a<NA>();
+          if (tid < 2 * L * nv) {
+            const float2 val = virtual_pilot(nv, P.vp_mx, P.vp_den, m.vp_mod[l][end], m.vp_ph[l][end], k);
+            if (end) x[nv + N + (nv - 1 - k)] = val;
+            else x[k] = val;
           }
         }
-        sync_a();
+        sync_a<NA>();
         if (hh == 0 && it >= 1) bar_sync(kBarEmpty, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
         // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493)
         for (int idx = tid; idx < N * L; idx += kThreads) {
@@ -470,7 +476,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
           hbuf[idx] = make_float2(float(ar), float(ai));
         }
-        sync_a();
+        sync_a<NA>();
         if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
           for (int idx = tid; idx < N * L; idx += kThreads) {
             const int l = idx / N, i = idx - l * N;
@@ -479,12 +485,12 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             ext[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
                                    float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
           }
-          sync_a();
+          sync_a<NA>();
           for (int idx = tid; idx < N * L; idx += kThreads) {
             const float2 s0 = hbuf[idx], lp = ext[idx];
             hbuf[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
           }
-          sync_a();
+          sync_a<NA>();
         }
       }
 
@@ -509,15 +515,15 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           } else {
             for (int idx = tid; idx < nl * M; idx += kThreads) ext[idx] = make_float2(0.f, 0.f);
-            sync_a();
+            sync_a<NA>();
             for (int idx = tid; idx < nl * N; idx += kThreads) {
               const int l = idx / N, i = idx - l * N;
               const int q = i / R;
               ext[l * M + q * kNRE + posl[i - q * R] - posl[0]] = hbuf[(lb + l) * N + i];
             }
           }
-          sync_a();
-          fft_dif_inverse(ext, nl, M, log2M, P.twiddle);
+          sync_a<NA>();
+          fft_dif_inverse<NA>(ext, nl, M, log2M, P.twiddle);
           for (int t = tid; t < 2 * SRSCE_TA_WINDOW; t += kThreads) {
             const int bin = (t < SRSCE_TA_WINDOW) ? t : SRSCE_TA_FFT - 2 * SRSCE_TA_WINDOW + t;
             const int pos = dif_position(bin & (M - 1), M);
@@ -528,7 +534,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
             m.prof[t] = acc;
           }
-          sync_a();
+          sync_a<NA>();
         }
         if (warp == 0) {
           // first maximum of each window; ties keep the lower index, as torch.max / np.argmax
@@ -580,14 +586,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           rsrp_part += t.x * t.x + t.y * t.y;
         }
         double v[3] = {double(epre_part), double(noise_part), double(rsrp_part)};
-        block_sum<3>(m, v);
+        block_sum<NA, 3>(m, v);
         if (tid == 0) {
           m.acc[0] += double(float(m.tot[0]));
           m.acc[1] += double(float(m.tot[1]));
           m.acc[2] += beta_d * beta_d * double(float(m.tot[2])) * double(S);
         }
       }
-      sync_a();
+      sync_a<NA>();
     }  // hops
 
     if (dbg & 1) {                                            // profiling ablation: writers run on stale pilots
@@ -609,7 +615,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   }
   } else {
   // ================================== writer warps ============================================
-  const int wb = warp - kWarps;
+  const int wb = warp - NA / 32;
   const long long n_iter = (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   int it = 0;
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
@@ -668,11 +674,12 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 } else {
                   const int T = P.fill_terms;
                   const int bands = H.band_sc1 - H.band_sc0;
-                  const int k0 = __ldg(P.fill_idx + g * bands + br);
-                  const float* cf = P.fill_coef + ((long long)g * bands + br) * T;
+                  const bool interior = P.fill_periodic && br >= kCnnEdgeRows && br < bands - kCnnEdgeRows;
+                  const int k0 = interior ? m.cnn_idx0[g][pos] + q * R : __ldg(P.fill_idx + g * bands + br);
+                  const float* cf = interior ? m.cnn_coef[g][pos] : P.fill_coef + ((long long)g * bands + br) * T;
                   v0 = make_float2(0.f, 0.f);
                   for (int t = 0; t < T; ++t) {
-                    const float w = __ldg(cf + t);
+                    const float w = cf[t];
                     const float2 a = ha[k0 + t];
                     v0.x += w * a.x;
                     v0.y += w * a.y;
@@ -757,13 +764,19 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
                          double, float2*, double*, long long, int);
 
-KernelFn pick_kernel(int vec, bool two_hops, bool has_rot) {
+template <int NA>
+KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
   if (vec == 2) {
-    if (two_hops) return has_rot ? estimate_kernel<2, true, true> : estimate_kernel<2, true, false>;
-    return has_rot ? estimate_kernel<2, false, true> : estimate_kernel<2, false, false>;
+    if (two_hops) return has_rot ? estimate_kernel<NA, 2, true, true> : estimate_kernel<NA, 2, true, false>;
+    return has_rot ? estimate_kernel<NA, 2, false, true> : estimate_kernel<NA, 2, false, false>;
   }
-  if (two_hops) return has_rot ? estimate_kernel<1, true, true> : estimate_kernel<1, true, false>;
-  return has_rot ? estimate_kernel<1, false, true> : estimate_kernel<1, false, false>;
+  if (two_hops) return has_rot ? estimate_kernel<NA, 1, true, true> : estimate_kernel<NA, 1, true, false>;
+  return has_rot ? estimate_kernel<NA, 1, false, true> : estimate_kernel<NA, 1, false, false>;
+}
+
+KernelFn pick_kernel(const PlanDev& v) {
+  const bool rot = v.cfo_compensate && v.cfo_defined;
+  return v.est_threads == 512 ? pick_kernel_na<512>(v.vec, v.n_hops == 2, rot) : pick_kernel_na<256>(v.vec, v.n_hops == 2, rot);
 }
 
 // Ablation switch for profiling only (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B);
@@ -795,9 +808,11 @@ int upload_plan(Plan& p, std::string& err) {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) { err = cuda_msg("cudaGetDevice", e); return SRSCE_ERR_CUDA; }
 
-  std::vector<float2> tw(SRSCE_TA_FFT);
-  for (int k = 0; k < SRSCE_TA_FFT; ++k) {
-    const double a = 2.0 * M_PI * double(k) / double(SRSCE_TA_FFT);
+  // twiddles of the transform this plan runs, dense (M entries), so that the first radix-4 pass walks
+  // them with unit stride and the whole table occupies M * 8 bytes of L1
+  std::vector<float2> tw(p.dev.fft_size);
+  for (int k = 0; k < p.dev.fft_size; ++k) {
+    const double a = 2.0 * M_PI * double(k) / double(p.dev.fft_size);
     tw[k] = make_float2(float(cos(a)), float(sin(a)));
   }
   if ((e = cudaMalloc(&p.d_twiddle, tw.size() * sizeof(float2))) != cudaSuccess) { err = cuda_msg("cudaMalloc", e); return SRSCE_ERR_CUDA; }
@@ -820,7 +835,7 @@ int upload_plan(Plan& p, std::string& err) {
     p.dev.fill_idx = static_cast<const int32_t*>(p.d_fill_idx);
     p.dev.fill_coef = static_cast<const float*>(p.d_fill_coef);
   }
-  KernelFn fn = pick_kernel(p.dev.vec, p.dev.n_hops == 2, p.dev.cfo_compensate && p.dev.cfo_defined);
+  KernelFn fn = pick_kernel(p.dev);
   // the limit is per kernel variant, not per plan: always raise it to the architectural maximum so that
   // plans with different footprints can share a variant
   if ((e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem())) != cudaSuccess) {
@@ -828,7 +843,7 @@ int upload_plan(Plan& p, std::string& err) {
     return SRSCE_ERR_CUDA;
   }
   int per_sm = 0, sms = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), kCtaThreads, p.dev.smem_bytes)) != cudaSuccess ||
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), cta_threads(p.dev.est_threads), p.dev.smem_bytes)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
     err = cuda_msg("occupancy query", e);
     return SRSCE_ERR_CUDA;
@@ -856,10 +871,10 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   cudaGetDevice(&dev);
   if (dev != p.device) { err = "plan was created on another CUDA device"; return SRSCE_ERR_INVALID; }
   if (n_units == 0) return SRSCE_OK;
-  KernelFn fn = pick_kernel(p.dev.vec, p.dev.n_hops == 2, p.dev.cfo_compensate && p.dev.cfo_defined);
+  KernelFn fn = pick_kernel(p.dev);
   const long long cap = (long long)p.n_sms * p.ctas_per_sm;
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
-  fn<<<grid, kCtaThreads, p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+  fn<<<grid, cta_threads(p.dev.est_threads), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
       debug_mode());

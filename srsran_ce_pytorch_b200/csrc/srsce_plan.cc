@@ -416,6 +416,29 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     for (int g = 0; g < G; ++g)
       emit_rows(all[g], N, terms, &p.fill_idx[size_t(g) * p.band_rows], &p.fill_coef[size_t(g) * p.band_rows * terms]);
     v.fill_terms = (d.fill == SRSCE_FILL_CNN) ? terms : 2;
+    // Away from the band edges every PRB sees the same neighbourhood, so the operator rows repeat with
+    // the PRB period (pilot index advancing by R per PRB).  Verify that bit for bit; if it holds the
+    // kernel keeps one PRB's rows in shared memory and only looks the edge rows up in global memory.
+    v.fill_periodic = 0;
+    if (d.fill == SRSCE_FILL_CNN && p.band_rows >= 2 * kCnnEdgeRows + kNRE) {
+      bool ok = true;
+      for (int g = 0; g < G && ok; ++g) {
+        const int32_t* idx = &p.fill_idx[size_t(g) * p.band_rows];
+        const float* coef = &p.fill_coef[size_t(g) * p.band_rows * terms];
+        const int q0 = kCnnEdgeRows / kNRE;
+        for (int pos = 0; pos < kNRE; ++pos) {
+          v.cnn_idx0[g][pos] = idx[kCnnEdgeRows + pos] - q0 * R;
+          for (int t = 0; t < kMaxFillTerms; ++t)
+            v.cnn_coef[g][pos][t] = (t < terms) ? coef[size_t(kCnnEdgeRows + pos) * terms + t] : 0.f;
+        }
+        for (int r = kCnnEdgeRows; r < p.band_rows - kCnnEdgeRows && ok; ++r) {
+          const int q = r / kNRE, pos = r - q * kNRE;
+          ok = idx[r] == v.cnn_idx0[g][pos] + q * R;
+          for (int t = 0; t < terms && ok; ++t) ok = coef[size_t(r) * terms + t] == v.cnn_coef[g][pos][t];
+        }
+      }
+      v.fill_periodic = ok ? 1 : 0;
+    }
   }
 
   // shared memory: smoothed pilots of every hop | staged pilot REs of this and the next unit |
@@ -426,15 +449,24 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     int ext = (N + 2 * v.n_virtual + 2 * (v.n_taps / 2)) * L;      // FIR input incl. virtual pilots and zero margins
     ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
     ext = std::max(ext, N * L);                                   // scratch of the CNN blend
-    const int tile_elems = kWarpsB * kTileRows * L * n_hops;
     auto up16 = [](int bytes) { return ((bytes + 15) / 16) * 16; };
     v.ext_elems = ext;
     v.off_h = 0;
     v.off_y = v.off_h + up16(h_elems * 8);
     v.off_ext = v.off_y + up16(y_elems * 8);
     v.off_tile = v.off_ext + up16(ext * 8);
-    v.off_misc = v.off_tile + up16(tile_elems * 8);
-    v.smem_bytes = v.off_misc + kMiscBytes;
+    // Two CTAs of 256 estimator threads (+4 writer warps) per SM when they fit, else one CTA of 512 (+8).
+    // The two-CTA footprint is held under the 196 KB shared-memory carve-out (1 KB per CTA is reserved by
+    // the system): one step higher leaves 28 KB instead of 60 KB of L1 for the twiddle / pilot loads of
+    // phase A, which was measured to cost 11 % of the headline throughput.
+    v.est_threads = 256;
+    for (;;) {
+      const int tile_elems = writer_warps(v.est_threads) * kTileRows * L * n_hops;
+      v.off_misc = v.off_tile + up16(tile_elems * 8);
+      v.smem_bytes = v.off_misc + kMiscBytes;
+      if (v.est_threads == 512 || 2 * (v.smem_bytes + 1024) <= 196 * 1024) break;
+      v.est_threads = 512;
+    }
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }
