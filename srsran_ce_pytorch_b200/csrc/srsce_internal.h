@@ -16,15 +16,15 @@ namespace srsce {
 constexpr int kNRE = 12;              // resource elements per PRB
 // A CTA = NA estimator threads (phase A: pilots -> smoothed channel + scalars) + writer warps (phase B:
 // interpolate + stream the dense grid out).  Geometries whose shared-memory footprint allows two CTAs
-// per SM run NA = 256 (+4 writer warps); heavier ones run one CTA of NA = 512 (+8 writer warps).
+// per SM run NA = 256 (+6 writer warps); heavier ones run one CTA of NA = 512 (+8 writer warps).
 constexpr int kMaxWarpsA = 16;
 constexpr int kMaxWarpsB = 8;
-constexpr int writer_warps(int na) { return na == 256 ? 4 : 8; }
+constexpr int writer_warps(int na) { return na == 256 ? 6 : 8; }
 constexpr int cta_threads(int na) { return na + 32 * writer_warps(na); }
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
 constexpr int kCnnEdgeRows = 2 * kNRE; // band rows at either end whose CNN operator rows are looked up individually
-constexpr int kMiscBytes = 8192;      // shared-memory slot of the kernel's small tables / reduction scratch
+constexpr int kMiscBytes = 6912;      // shared-memory slot of the kernel's small tables / reduction scratch
 
 // One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
 // a subcarrier at position p of PRB q takes pilots q*R+jl and q*R+jr of its CDM group

@@ -219,12 +219,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //                              EF = N + 2*nv + 2*pad; later the FFT scratch
 //   tiles[writer warp][hop][32][L]  interpolated rows being streamed out
 template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT>
-__global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 4 : 8), NA == 256 ? 2 : 1)
+__global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 6 : 8), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg) {
   constexpr int kThreads = NA;                              // estimator threads
-  constexpr int kWarpsB = (NA == 256) ? 4 : 8;            // = writer_warps(NA)
+  constexpr int kWarpsB = (NA == 256) ? 6 : 8;            // = writer_warps(NA)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
   extern __shared__ __align__(16) unsigned char smem[];
   float2* const hall = reinterpret_cast<float2*>(smem + P.off_h);

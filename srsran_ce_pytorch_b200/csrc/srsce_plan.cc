@@ -455,7 +455,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     v.off_y = v.off_h + up16(h_elems * 8);
     v.off_ext = v.off_y + up16(y_elems * 8);
     v.off_tile = v.off_ext + up16(ext * 8);
-    // Two CTAs of 256 estimator threads (+4 writer warps) per SM when they fit, else one CTA of 512 (+8).
+    // Two CTAs of 256 estimator threads (+6 writer warps) per SM when they fit, else one CTA of 512 (+8).
     // The two-CTA footprint is held under the 196 KB shared-memory carve-out (1 KB per CTA is reserved by
     // the system): one step higher leaves 28 KB instead of 60 KB of L1 for the twiddle / pilot loads of
     // phase A, which was measured to cost 11 % of the headline throughput.
