@@ -36,16 +36,28 @@ METRIC = "SRS channel estimates/sec (UE x port x rx-ant) at 273 PRB"
 UNIT = "estimates/s"
 N_PRB, N_SYM, LAYERS, RX_ANT, UES, PILOT_SYMBOLS = 273, 14, 4, 4, 64, (13,)
 UNITS_PER_SLOT = RX_ANT * UES
+WORKLOAD = "config2"
+
+
+def select_workload(name, slots):
+    """config2 (headline): 4 rx x 64 UEs per slot.  config3: massive-MIMO, 64 rx x 128 UEs per slot
+    (BASELINE.json configs[2]; its 1024 slots are streamed `slots` at a time through one reused output buffer)."""
+    global RX_ANT, UES, UNITS_PER_SLOT, WORKLOAD
+    WORKLOAD = name
+    if name == "config3":
+        RX_ANT, UES = 64, 128
+    UNITS_PER_SLOT = RX_ANT * UES
+    return slots if slots else (64 if name == "config2" else 2)
 
 
 def workload_config(slots, e2e_slots=None):
-    cfg = {"workload": "config2: ce_rule_tensorized batched, 273 PRB 30 kHz, 4 ports, 4 rx antennas, comb-4, "
-                       "64 UEs per slot, 1 pilot symbol, 14-symbol grid, filter smoothing, CFO compensation on",
-           "units_per_step": slots * UNITS_PER_SLOT, "slots_per_step": slots, "estimates_per_unit": LAYERS,
+    cfg = {"workload": f"{WORKLOAD}: ce_rule_tensorized batched, 273 PRB 30 kHz, 4 ports, {RX_ANT} rx antennas, comb-4, "
+                       f"{UES} UEs per slot, 1 pilot symbol, 14-symbol grid, filter smoothing, CFO compensation on",
+           "units_per_step_per_gpu": slots * UNITS_PER_SLOT, "slots_per_step_per_gpu": slots, "estimates_per_unit": LAYERS,
            "rx_layout": "reference ([n_sc, n_sym] row major per unit, one grid per unit)",
            "l2_policy": "inputs+outputs per step (>= 7 GB) exceed the 126 MB L2; no flush needed"}
     if e2e_slots is not None:
-        cfg["e2e_units_per_step"] = e2e_slots * UNITS_PER_SLOT
+        cfg["e2e_units_per_step"] = min(e2e_slots * UNITS_PER_SLOT, slots * UNITS_PER_SLOT, 2048)
     return cfg
 
 
@@ -64,10 +76,11 @@ def algorithmic_bytes_per_unit():
 # --------------------------------------------------------------------------------------------
 # CPU arm (oracle port on all host cores)
 # --------------------------------------------------------------------------------------------
-def cpu_pool(n_distinct=16):
+def cpu_pool(n_distinct=None):
     from oracle import ce_oracle, cpu_bench
     from srsran_ce_pytorch_b200 import synth
     hop1, hop2, cfg = geometry()
+    n_distinct = n_distinct or max(16, RX_ANT)
     d = synth.make_units(hop1, hop2, cfg, LAYERS, n_distinct, pilot_share=RX_ANT, seed=4321)
     return cpu_bench.OraclePool(d["rx"].numpy(), d["pilots"].numpy(), RX_ANT, 1.0, ce_oracle.hop_from_any(hop1),
                                 ce_oracle.HopSpec.absent(), ce_oracle.est_from_any(cfg))
@@ -288,7 +301,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer entry point
     e2e_slots = min(args.e2e_slots, args.slots)
-    n_e2e = e2e_slots * UNITS_PER_SLOT
+    n_e2e = min(e2e_slots * UNITS_PER_SLOT, n_local, 2048)     # <= 3 GB of pinned output
     h_rx = rx[:n_e2e].cpu().pin_memory()
     h_pil = pil[:n_e2e // RX_ANT].cpu().pin_memory()
     h_out = torch.empty((n_e2e, 12 * N_PRB, N_SYM, LAYERS), dtype=torch.complex64).pin_memory()
@@ -353,12 +366,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--slots", type=int, default=64, help="slots (x256 units) per step and per GPU")
+    ap.add_argument("--slots", type=int, default=0, help="slots per step and per GPU (default: 64 for config2, 2 for config3)")
+    ap.add_argument("--workload", choices=["config2", "config3"], default="config2")
     ap.add_argument("--e2e-slots", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-layout", action="store_true")
     args = ap.parse_args()
+    args.slots = select_workload(args.workload, args.slots)
     if args.impl == "reference":
         run_reference(args)
     else:

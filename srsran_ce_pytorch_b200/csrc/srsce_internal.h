@@ -24,7 +24,7 @@ constexpr int cta_threads(int na) { return na + 32 * writer_warps(na); }
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
 constexpr int kCnnEdgeRows = 2 * kNRE; // band rows at either end whose CNN operator rows are looked up individually
-constexpr int kMiscBytes = 6912;      // shared-memory slot of the kernel's small tables / reduction scratch
+constexpr int kMiscBytes = 7680;      // shared-memory slot of the kernel's small tables / reduction scratch
 
 // One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
 // a subcarrier at position p of PRB q takes pilots q*R+jl and q*R+jr of its CDM group
@@ -69,6 +69,7 @@ struct PlanDev {
   int32_t cols;            // row_elems / vec store slots per row
   int32_t blend;           // CNN blend of the smoothed pilots active (ce_dl_cnn.py:712-717)
   int32_t est_threads;     // NA: 256 (two CTAs per SM) or 512 (one CTA per SM)
+  int32_t hall_bufs;       // 1: writers and the next unit's FIR alternate on one pilot buffer; 2: double buffered
   // shared-memory carve-up (byte offsets from the dynamic smem base)
   int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
   float cnn_alpha;

@@ -34,10 +34,11 @@ namespace srsce {
 
 namespace {
 
-struct ColInfo {           // one store slot of an output row (VEC consecutive complex64 elements)
+struct ColInfo {           // one store slot of an output row (VEC consecutive complex64 elements); 24 bytes
   float2 rot[2];           // final CFO rotation of each element's symbol
-  int32_t layer[2];
-  int32_t flags[2];        // bit0: symbol inside hop-1 allocation, bit1: inside hop-2 allocation
+  uint8_t layer[2];
+  uint8_t flags[2];        // bit0: symbol inside hop-1 allocation, bit1: inside hop-2 allocation
+  uint8_t pad[4];
 };
 
 struct Misc {
@@ -54,7 +55,7 @@ struct Misc {
   int32_t cnn_idx0[2][kNRE];
   float vp_mod[SRSCE_MAX_LAYERS][2][12];   // modulus / phase of the edge pilots (virtual-pilot regression)
   float vp_ph[SRSCE_MAX_LAYERS][2][12];
-  ColInfo col[SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];
+  ColInfo col[2][SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];   // one store-slot table per hall buffer
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
 
@@ -69,8 +70,8 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
 // Named barriers: 0 is __syncthreads (whole CTA); 1 joins the estimator warps only; 2 ("full") hands
-// hall + the store-slot table from the estimator warps to the writer warps, 3 ("empty") hands them back.
-constexpr int kBarA = 1, kBarFull = 2, kBarEmpty = 3;
+// hall[b] + store-slot table b from the estimator warps to the writer warps, 4+b ("empty") hands them back.
+constexpr int kBarA = 1, kBarFull = 2, kBarEmpty = 4;   // + buffer index (0/1)
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 template <int NA>
@@ -227,7 +228,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   constexpr int kWarpsB = (NA == 256) ? 6 : 8;            // = writer_warps(NA)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
   extern __shared__ __align__(16) unsigned char smem[];
-  float2* const hall = reinterpret_cast<float2*>(smem + P.off_h);
+  float2* const hall0 = reinterpret_cast<float2*>(smem + P.off_h);     // hall_bufs buffers of n_hops*L*N
   float2* const ystage = reinterpret_cast<float2*>(smem + P.off_y);
   float2* const tiles = reinterpret_cast<float2*>(smem + P.off_tile);
   float2* const ext = reinterpret_cast<float2*>(smem + P.off_ext);
@@ -275,22 +276,22 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     for (int k = tid; k < pil_lines; k += kThreads) prefetch_l2(pn + ((long long)k << 7));
   };
   // store-slot table of the writer warps: layer / allocation flags / final CFO rotation of every slot
-  auto build_store_table = [&]() {
+  auto build_store_table = [&](ColInfo* colw) {
     for (int c = tid; c < cols; c += kThreads) {
       ColInfo ci;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int el = min(c * VEC + e, row_elems - 1);
         const int sym = el / L;
-        ci.layer[e] = el - sym * L;
+        ci.layer[e] = uint8_t(el - sym * L);
         int f = (sym >= P.hop[0].start_symbol && sym < P.hop[0].end_symbol) ? 1 : 0;
         if (TWO_HOPS && sym >= P.hop[1].start_symbol && sym < P.hop[1].end_symbol) f |= 2;
-        ci.flags[e] = f;
+        ci.flags[e] = uint8_t(f);
         double sn = 0.0, cs = 1.0;
         if (HAS_ROT) sincos(2.0 * M_PI * P.t_sym[sym] * m.acc[4], &sn, &cs);   // :922-929
         ci.rot[e] = make_float2(float(cs), float(sn));
       }
-      m.col[c] = ci;
+      colw[c] = ci;
     }
   };
   stage_unit(blockIdx.x, ystage);
@@ -302,6 +303,9 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
     const float2* const ys = ystage + (it & 1) * ylen;
+    const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
+    float2* const hall = hall0 + hb_idx * (n_hops * L * N);
+    const bool wait_empty = it >= P.hall_bufs;                 // the writers last used this buffer hall_bufs units ago
     stage_unit(u + gridDim.x, ystage + ((it + 1) & 1) * ylen);
     cp_async_commit();
     if (tid < 8) m.acc[tid] = 0.0;
@@ -360,7 +364,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 
       // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584)
       float epre_part = 0.f;
-      if (!filt && hh == 0 && it >= 1) bar_sync(kBarEmpty, kCtaThreads);   // LS writes hall: writers must be done with it
+      if (!filt && hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // LS writes hall: writers must be done with it
       {
         float2* const dst = filt ? ext + pad + nv : hbuf;
         const int dstride = filt ? EF : N;
@@ -462,7 +466,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
         }
         sync_a<NA>();
-        if (hh == 0 && it >= 1) bar_sync(kBarEmpty, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
+        if (hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
         // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493)
         for (int idx = tid; idx < N * L; idx += kThreads) {
           const int l = idx / N, i = idx - l * N;
@@ -498,8 +502,8 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       //      rotation :922-929, allocation flags) and release the writer warps; the time alignment
       //      and noise estimates below only read hall, concurrently with them
       if (hh == n_hops - 1) {
-        build_store_table();
-        bar_arrive(kBarFull, kCtaThreads);
+        build_store_table(m.col[hb_idx]);
+        bar_arrive(kBarFull + hb_idx, kCtaThreads);
       }
 
       // ---- time alignment (:674-698)
@@ -597,9 +601,9 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     }  // hops
 
     if (dbg & 1) {                                            // profiling ablation: writers run on stale pilots
-      if (it >= 1) bar_sync(kBarEmpty, kCtaThreads);
-      build_store_table();
-      bar_arrive(kBarFull, kCtaThreads);
+      if (wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);
+      build_store_table(m.col[hb_idx]);
+      bar_arrive(kBarFull + hb_idx, kCtaThreads);
     }
     // ---- per-unit scalars (:899-919, :932-937)
     if (tid == 0) {
@@ -619,8 +623,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   const long long n_iter = (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   int it = 0;
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-    const ColInfo* const colb = m.col;
-    bar_sync(kBarFull, kCtaThreads);
+    const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
+    const float2* const hall = hall0 + hb_idx * (n_hops * L * N);
+    const ColInfo* const colb = m.col[hb_idx];
+    bar_sync(kBarFull + hb_idx, kCtaThreads);
     // ===================================== phase B ==========================================
     // Each warp takes 32 consecutive subcarriers: lane r interpolates row r into the warp's tile
     // ([hop][row][layer]), then the warp streams the rows out, every lane owning a fixed store
@@ -756,7 +762,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
     }
-    if (it + 1 < n_iter) bar_arrive(kBarEmpty, kCtaThreads);         // hall / store table may be rewritten
+    if (it + P.hall_bufs < n_iter) bar_arrive(kBarEmpty + hb_idx, kCtaThreads);   // this buffer may be rewritten
   }
   }
 }

@@ -451,22 +451,25 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     ext = std::max(ext, N * L);                                   // scratch of the CNN blend
     auto up16 = [](int bytes) { return ((bytes + 15) / 16) * 16; };
     v.ext_elems = ext;
-    v.off_h = 0;
-    v.off_y = v.off_h + up16(h_elems * 8);
-    v.off_ext = v.off_y + up16(y_elems * 8);
-    v.off_tile = v.off_ext + up16(ext * 8);
     // Two CTAs of 256 estimator threads (+6 writer warps) per SM when they fit, else one CTA of 512 (+8).
     // The two-CTA footprint is held under the 196 KB shared-memory carve-out (1 KB per CTA is reserved by
     // the system): one step higher leaves 28 KB instead of 60 KB of L1 for the twiddle / pilot loads of
     // phase A, which was measured to cost 11 % of the headline throughput.
-    v.est_threads = 256;
-    for (;;) {
-      const int tile_elems = writer_warps(v.est_threads) * kTileRows * L * n_hops;
+    auto layout = [&](int na, int bufs) {
+      const int tile_elems = writer_warps(na) * kTileRows * L * n_hops;
+      v.est_threads = na;
+      v.hall_bufs = bufs;
+      v.off_h = 0;
+      v.off_y = v.off_h + up16(bufs * h_elems * 8);
+      v.off_ext = v.off_y + up16(y_elems * 8);
+      v.off_tile = v.off_ext + up16(ext * 8);
       v.off_misc = v.off_tile + up16(tile_elems * 8);
       v.smem_bytes = v.off_misc + kMiscBytes;
-      if (v.est_threads == 512 || 2 * (v.smem_bytes + 1024) <= 196 * 1024) break;
-      v.est_threads = 512;
-    }
+    };
+    layout(256, 1);
+    if (2 * (v.smem_bytes + 1024) > 196 * 1024) layout(512, 1);
+    // (double buffering the smoothed pilots of a single resident CTA -- layout(512, 2) -- was measured
+    //  slower on B200: the larger carve-out leaves less L1 for phase A's pilot / twiddle loads)
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }
