@@ -10,7 +10,7 @@
  * pointers and sizes only, no torch types, no C++ exceptions across the boundary.
  *
  * Ownership / threading contract
- *   - The caller owns every device buffer passed to srsce_estimate / srsce_cnn_fill and keeps it
+ *   - The caller owns every device buffer passed to srsce_estimate / srsce_estimate_compact and keeps it
  *     alive until the stream reaches the kernel.  The library allocates nothing per call, never
  *     synchronises and never touches the default stream unless it is the stream passed in.
  *   - A plan owns its (small) host tables and their device copies; it is immutable after creation
@@ -106,7 +106,7 @@ int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info);
 /* Host-side tables (for tests of the host logic; no device needed).
  *   taps:      n_taps doubles                       get_rc_filter (:184-234)
  *   fill_idx:  n_hop_sc * n_cdm int32               first pilot index of each band subcarrier's operator row
- *   fill_coef: n_hop_sc * n_cdm * fill_terms float  operator coefficients (lerp: {1-a, a} encoded as {a})
+ *   fill_coef: n_hop_sc * n_cdm * fill_terms float  operator coefficients (linear fill: the row {1-a, a} of the lerp)
  * Pass NULL to skip a table. */
 int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, float* fill_coef);
 
@@ -126,6 +126,18 @@ int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, f
 int srsce_estimate(const srsce_plan* plan, const void* rx_grid, const int64_t rx_strides[3],
                    const void* pilots, int32_t pilot_share, double beta, void* ch_est,
                    double* scalars, int64_t n_units, void* stream);
+
+/* Compact-output variant (NOT part of the reference contract).  The reference spends
+ * 13/14 of its output bytes replicating one column over the allocated symbols
+ * (ce_rule_tensorized.py:346-347) and rotating it per symbol (:922-929).  This entry point returns the
+ * factors instead:
+ *   ch_sc    complex64 [n_units][n_hops][n_sc][n_layers]  interpolated channel of each hop (0 outside its band)
+ *   sym_rot  complex64 [n_units][n_sym]                   final CFO rotation of each symbol (1 when none applies)
+ * so that   channel_est_rg[sc][t][l] = sym_rot[t] * (hop-2 value if t is in hop 2's allocated symbols and sc in its
+ * band, else hop-1 value if t is in hop 1's allocated symbols, else 0).  Everything else as srsce_estimate. */
+int srsce_estimate_compact(const srsce_plan* plan, const void* rx_grid, const int64_t rx_strides[3],
+                           const void* pilots, int32_t pilot_share, double beta, void* ch_sc, void* sym_rot,
+                           double* scalars, int64_t n_units, void* stream);
 
 /* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
 int srsce_last_launch_count(void);

@@ -116,7 +116,8 @@ int upload_plan(Plan& p, std::string& err);
 void release_plan(Plan& p);
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots,
                     int pilot_share, double beta, void* out, double* scalars, int64_t n_units,
-                    void* stream, int* launches, std::string& err);
+                    void* stream, int* launches, std::string& err, void* out_compact = nullptr,
+                    void* rot_compact = nullptr);
 int max_dynamic_smem();
 
 }  // namespace srsce

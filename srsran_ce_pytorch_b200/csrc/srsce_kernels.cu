@@ -223,7 +223,8 @@ template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT>
 __global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 6 : 8), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
-                float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg) {
+                float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg,
+                float2* __restrict__ out_c, float2* __restrict__ rot_c) {
   constexpr int kThreads = NA;                              // estimator threads
   constexpr int kWarpsB = (NA == 256) ? 6 : 8;            // = writer_warps(NA)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
@@ -292,6 +293,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         ci.rot[e] = make_float2(float(cs), float(sn));
       }
       colw[c] = ci;
+    }
+  };
+  // compact output: the per-symbol final CFO rotation goes out as a [n_sym] vector instead of being multiplied in
+  auto write_symbol_rotation = [&](long long unit) {
+    if (rot_c != nullptr && tid < P.n_sym) {
+      double sn = 0.0, cs = 1.0;
+      if (HAS_ROT) sincos(2.0 * M_PI * P.t_sym[tid] * m.acc[4], &sn, &cs);
+      rot_c[unit * P.n_sym + tid] = make_float2(float(cs), float(sn));
     }
   };
   stage_unit(blockIdx.x, ystage);
@@ -503,6 +512,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       //      and noise estimates below only read hall, concurrently with them
       if (hh == n_hops - 1) {
         build_store_table(m.col[hb_idx]);
+        write_symbol_rotation(u);
         bar_arrive(kBarFull + hb_idx, kCtaThreads);
       }
 
@@ -704,6 +714,20 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
         __syncwarp();
 
+        if (out_c != nullptr) {
+          // compact output [unit][hop][subcarrier][layer]: every lane writes the row it interpolated
+          if (row < n_sc) {
+#pragma unroll
+            for (int hh = 0; hh < n_hops; ++hh) {
+              float2* d = out_c + (((long long)u * n_hops + hh) * n_sc + row) * L;
+              const bool have = (((hh == 0) ? in1 : in2) >> lane) & 1u;
+              const float2* t = tile0 + (hh * kTileRows + lane) * L;
+              for (int l = 0; l < L; ++l) __stcs(d + l, have ? t[l] : make_float2(0.f, 0.f));
+            }
+          }
+          continue;
+        }
+
         if (fast) {
           if (lane_on) {
             float2* dst = outu + (long long)(row0 + my_rs) * row_elems + my_c * VEC;
@@ -768,7 +792,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 }
 
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
-                         double, float2*, double*, long long, int);
+                         double, float2*, double*, long long, int, float2*, float2*);
 
 template <int NA>
 KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
@@ -870,7 +894,7 @@ void release_plan(Plan& p) {
 
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots, int pilot_share,
                     double beta, void* out, double* scalars, int64_t n_units, void* stream, int* launches,
-                    std::string& err) {
+                    std::string& err, void* out_compact, void* rot_compact) {
   *launches = 0;
   if (p.device < 0) { err = "plan has no CUDA device (created without a GPU); there is no CPU compute path"; return SRSCE_ERR_NO_DEVICE; }
   int dev = -1;
@@ -883,7 +907,7 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   fn<<<grid, cta_threads(p.dev.est_threads), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
-      debug_mode());
+      debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = cuda_msg("kernel launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;

@@ -126,6 +126,56 @@ class Plan:
         return out, scalars
 
 
+    def _check_inputs(self, rx, pilots, pilot_share):
+        i = self.info
+        if not rx.is_cuda or not pilots.is_cuda:
+            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
+        if rx.dtype != torch.complex64 or pilots.dtype != torch.complex64:
+            raise TypeError("rx and pilots must be complex64")
+        if rx.dim() != 3 or tuple(rx.shape[1:]) != (i.n_sc, i.n_sym):
+            raise IndexError(f"received grid shape {tuple(rx.shape)} != [B, {i.n_sc}, {i.n_sym}]")
+        n_units = int(rx.shape[0])
+        if pilot_share < 1 or n_units % pilot_share:
+            raise ValueError("number of units must be a multiple of pilot_share")
+        want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
+        if tuple(pilots.shape) != want:
+            raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
+        return n_units, (pilots if pilots.is_contiguous() else pilots.contiguous())
+
+    def estimate_compact(self, rx: torch.Tensor, pilots: torch.Tensor, beta: float, pilot_share: int = 1):
+        """Compact output (not part of the reference contract): returns (ch_sc [B, n_hops, n_sc, L],
+        sym_rot [B, n_sym], scalars [B, 6]); ``expand_compact`` rebuilds the dense grid."""
+        i = self.info
+        n_units, pilots = self._check_inputs(rx, pilots, pilot_share)
+        n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
+        ch = torch.empty((n_units, n_hops, i.n_sc, i.n_layers), dtype=torch.complex64, device=rx.device)
+        rot = torch.empty((n_units, i.n_sym), dtype=torch.complex64, device=rx.device)
+        scalars = torch.empty((n_units, 6), dtype=torch.float64, device=rx.device)
+        strides = (C.c_int64 * 3)(*rx.stride())
+        with torch.cuda.device(rx.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.raise_for(lib.srsce_estimate_compact(self._h, rx.data_ptr(), strides, pilots.data_ptr(),
+                                                      int(pilot_share), float(beta), ch.data_ptr(), rot.data_ptr(),
+                                                      scalars.data_ptr(), n_units, C.c_void_p(stream)))
+        return ch, rot, scalars
+
+    def expand_compact(self, ch: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
+        """[B, n_hops, n_sc, L] x [B, n_sym] -> the dense [B, n_sc, n_sym, L] grid of the reference contract
+        (plain torch ops; for consumers and tests -- the fused dense path is ``estimate``)."""
+        i, d = self.info, self.desc
+        sym = torch.arange(i.n_sym, device=ch.device)
+        grid = torch.zeros((ch.shape[0], i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=ch.device)
+        for hh in range(ch.shape[1]):
+            h = d.hop[hh]
+            in_sym = (sym >= h.start_symbol) & (sym < h.start_symbol + h.n_alloc_symbols)
+            sc0, sc1 = 12 * h.prb_start, 12 * (h.prb_start + h.n_prbs)
+            if hh == 0:
+                grid[:, :, in_sym, :] = ch[:, 0, :, None, :].expand(-1, -1, int(in_sym.sum()), -1)
+            else:
+                grid[:, sc0:sc1, in_sym, :] = ch[:, hh, sc0:sc1, None, :].expand(-1, -1, int(in_sym.sum()), -1)
+        return grid * rot[:, None, :, None]
+
+
 _PLANS: dict = {}
 _PLANS_LOCK = threading.Lock()
 

@@ -187,3 +187,23 @@ def test_persistent_loop_many_units_per_cta():
             s = sc[b].cpu().numpy()
             tol.check_scalars([s[0], s[1], s[2], s[3], s[4] if s[5] else None], want[1:], 30e3, diag["ta_margin"],
                               tag=f"persistent/{two_hops}/{b}")
+
+
+@pytest.mark.parametrize("case", [BATCH_CASES[0], BATCH_CASES[3], BATCH_CASES[4], BATCH_CASES[6]], ids=["c0", "c3", "c4", "c6"])
+@pytest.mark.parametrize("fill", ["linear", "cnn"])
+def test_compact_output_expands_to_dense(case, fill):
+    """srsce_estimate_compact: factors [B, hops, n_sc, L] x [B, n_sym] rebuild the dense grid
+    of the reference contract; scalars are identical to the dense call."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    grid, start, n, syms, pat, L, sm, cfo, h2, share, sym_major = case
+    hop1 = synth.make_hop(grid, start, n, syms, pat, (L + 1) // 2, start_symbol=1, n_alloc=12)
+    hop2 = synth.no_hop() if h2 is None else synth.make_hop(grid, h2[0], n, h2[1], pat, (L + 1) // 2, start_symbol=5, n_alloc=9)
+    cfg = synth.make_config(30e3, sm, cfo)
+    data = synth.make_units(hop1, hop2, cfg, L, 4 * share, pilot_share=share, seed=11, device="cuda", symbol_major=sym_major)
+    plan = estimator.make_plan(grid, 14, L, hop1, hop2, cfg, fill)
+    dense, sc = plan.estimate(data["rx"], data["pilots"], 1.0, share)
+    ch, rot, sc2 = plan.estimate_compact(data["rx"], data["pilots"], 1.0, share)
+    assert ch.shape == (4 * share, 2 if h2 else 1, 12 * grid, L) and rot.shape == (4 * share, 14)
+    assert torch.equal(sc, sc2)
+    mx, nmse = tol.grid_errors(plan.expand_compact(ch, rot).cpu().numpy(), dense.cpu().numpy())
+    assert mx <= 1e-6 and nmse <= 1e-13, (mx, nmse)
