@@ -299,6 +299,22 @@ def run_ours(args):
                "kernel_ms": alt_ms, "n_gpus": 1}
         del rx_sm
 
+    # ---- compact output (srsce_estimate_compact, SURVEY 8f-2: outside the reference contract, reported separately)
+    compact = None
+    if not args.no_alt_layout:
+        for _ in range(3):
+            plan.estimate_compact(rx, pil, 1.0, RX_ANT)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(args.steps):
+            plan.estimate_compact(rx, pil, 1.0, RX_ANT)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / args.steps
+        compact = {"output": "[B, hops, n_sc, L] + [B, n_sym] factors instead of the dense grid",
+                   "value": LAYERS * n_local / (cms * 1e-3), "unit": UNIT, "kernel_ms": cms, "n_gpus": 1}
+
     # ---- end to end through the host-buffer entry point
     e2e_slots = min(args.e2e_slots, args.slots)
     n_e2e = min(e2e_slots * UNITS_PER_SLOT, n_local, 2048)     # <= 3 GB of pinned output
@@ -323,6 +339,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     e2e_ok = bool(torch.equal(h_sc[:64], sc[:64].cpu())) and bool(torch.equal(h_out[:8], out[:8].cpu()))
+    if compact is not None:
+        del h_out
+        pipe_c = HostPipeline(plan, 256, RX_ANT, dev, compact=True)
+        hc = (torch.empty((n_e2e, 1, 12 * N_PRB, LAYERS), dtype=torch.complex64).pin_memory(),
+              torch.empty((n_e2e, N_SYM), dtype=torch.complex64).pin_memory())
+        for _ in range(2):
+            pipe_c.run(h_rx, h_pil, 1.0, hc, h_sc)
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe_c.run(h_rx, h_pil, 1.0, hc, h_sc)
+        torch.cuda.synchronize()
+        compact["e2e_value"] = LAYERS * n_e2e * e2e_steps / (time.perf_counter() - w0)
+        compact["e2e_h2d_bytes_per_step"], compact["e2e_d2h_bytes_per_step"] = pipe_c.h2d_bytes, pipe_c.d2h_bytes
 
     if rank == 0:
         peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -335,7 +365,8 @@ def run_ours(args):
         traffic = None
         prof = ROOT / "profiles" / "traffic.json"
         if prof.exists():
-            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch_at_bench_size")
+            traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch_at_bench_size") if WORKLOAD == "config2" and \
+                args.slots == 64 else None
         line = {
             "metric": METRIC, "value": LAYERS * n_global * args.steps / (total_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
@@ -350,6 +381,8 @@ def run_ours(args):
                     "steps": e2e_steps, "units_per_step": n_e2e, "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": sampler.summary(wall0, wall1),
         }
+        if compact is not None:
+            line["compact_output"] = compact
         if alt is not None:
             alt["roofline_frac"] = bpu * n_local / (alt["kernel_ms"] * 1e-3) / 1e9 / peak
             line["alt_layout"] = alt
