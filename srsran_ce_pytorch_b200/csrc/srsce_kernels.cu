@@ -51,6 +51,7 @@ struct Misc {
   float prof[2 * SRSCE_TA_WINDOW];
   LerpEntry lerp[2][kNRE];
   int32_t re_pos[2][kNRE];
+  unsigned long long r_magic;
   float cnn_coef[2][kNRE][kMaxFillTerms];
   int32_t cnn_idx0[2][kNRE];
   float vp_mod[SRSCE_MAX_LAYERS][2][12];   // modulus / phase of the edge pilots (virtual-pilot regression)
@@ -103,8 +104,9 @@ __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
 }
 
 // Subcarrier of pilot i of CDM group g inside a hop band.
+// (i / R by multiply-shift: r_magic = ceil(2^32 / R) is exact for i < 2^16, R <= 12)
 __device__ __forceinline__ int pilot_sc(const Misc& m, int band_sc0, int R, int g, int i) {
-  const int q = i / R;
+  const int q = int((static_cast<unsigned long long>(static_cast<unsigned>(i)) * m.r_magic) >> 32);
   return band_sc0 + q * kNRE + m.re_pos[g][i - q * R];
 }
 
@@ -171,7 +173,7 @@ __device__ void fft_dif_inverse(float2* s, int nl, int M, int log2M, const float
     const int step = M >> log2n;                    // twiddle stride: w_n^j = tw[j * M / n], tw[k] = exp(+j 2 pi k / M)
     const int per_vec = M >> 2;
     for (int b = tid; b < nl * per_vec; b += NA) {
-      const int l = b / per_vec, r = b - l * per_vec;
+      const int l = b >> (log2M - 2), r = b & (per_vec - 1);
       const int blk = r >> log2q, j = r & (q - 1);
       float2* p = s + l * M + (blk << log2n) + j;
       const float2 a0 = p[0], a1 = p[q], a2 = p[2 * q], a3 = p[3 * q];
@@ -253,6 +255,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     m.re_pos[k / kNRE][k % kNRE] = P.re_pos[k / kNRE][k % kNRE];
     m.cnn_idx0[k / kNRE][k % kNRE] = P.cnn_idx0[k / kNRE][k % kNRE];
   }
+  if (tid == 0) m.r_magic = ((1ull << 32) + static_cast<unsigned>(R) - 1) / static_cast<unsigned>(R);
   for (int k = tid; k < 2 * kNRE * kMaxFillTerms; k += kThreads)
     (&m.cnn_coef[0][0][0])[k] = (&P.cnn_coef[0][0][0])[k];
   __syncthreads();
@@ -477,17 +480,27 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         sync_a<NA>();
         if (hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
         // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493)
-        for (int idx = tid; idx < N * L; idx += kThreads) {
-          const int l = idx / N, i = idx - l * N;
-          const float2* x = ext + l * EF + i + nv + 2 * pad;   // tap k multiplies x[-k]
-          double ar = 0.0, ai = 0.0;
-          for (int k = 0; k < K; ++k) {
-            const float2 t = x[-k];
-            const double w = m.taps[k];
-            ar += w * double(t.x);
-            ai += w * double(t.y);
+        // two adjacent outputs per thread share all but one of their input samples
+        for (int l = 0; l < L; ++l) {
+          const float2* const xl = ext + l * EF + nv + 2 * pad;    // tap k of output i multiplies xl[i - k]
+          float2* const hl = hbuf + l * N;
+          for (int i = 2 * tid; i < N; i += 2 * kThreads) {
+            double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+            const float2 t1 = (i + 1 < N) ? xl[i + 1] : make_float2(0.f, 0.f);
+            double tx1 = double(t1.x), ty1 = double(t1.y);
+            for (int k = 0; k < K; ++k) {
+              const float2 t0 = xl[i - k];
+              const double tx0 = double(t0.x), ty0 = double(t0.y), w = m.taps[k];
+              ar0 += w * tx0;
+              ai0 += w * ty0;
+              ar1 += w * tx1;
+              ai1 += w * ty1;
+              tx1 = tx0;
+              ty1 = ty0;
+            }
+            hl[i] = make_float2(float(ar0), float(ai0));
+            if (i + 1 < N) hl[i + 1] = make_float2(float(ar1), float(ai1));
           }
-          hbuf[idx] = make_float2(float(ar), float(ai));
         }
         sync_a<NA>();
         if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
