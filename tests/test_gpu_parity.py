@@ -207,3 +207,47 @@ def test_compact_output_expands_to_dense(case, fill):
     assert torch.equal(sc, sc2)
     mx, nmse = tol.grid_errors(plan.expand_compact(ch, rot).cpu().numpy(), dense.cpu().numpy())
     assert mx <= 1e-6 and nmse <= 1e-13, (mx, nmse)
+
+
+ODD_ROW_CASES = [
+    # n_sym, layers, pilot symbols, start_symbol, n_alloc  -> row_elems = n_sym * layers
+    (1, 1, [0], 0, 1),        # 1 element per row: 8-byte store path
+    (1, 3, [0], 0, 1),        # 3 elements
+    (7, 1, [3], 1, 5),        # 7 elements, partial allocation
+    (13, 3, [6], 0, 13),      # 39 store slots per row: more than one warp pass per row
+    (5, 3, [1, 3], 0, 5),     # two pilot symbols, CFO estimated but not compensated (grid is not 14 symbols)
+    (14, 3, [2, 11], 0, 14),  # even row (42 elements) but odd layer count: unpaired slots, with the final CFO rotation
+    (9, 2, [4], 2, 6),        # even row, 9 slots
+]
+
+
+@pytest.mark.parametrize("case", ODD_ROW_CASES, ids=[f"nsym{c[0]}-L{c[1]}" for c in ODD_ROW_CASES])
+@pytest.mark.parametrize("two_hops", [False, True], ids=["1hop", "2hop"])
+def test_short_and_odd_grids_match_oracle(case, two_hops):
+    """Grids that are not 14 symbols / rows with an odd number of elements exercise the scalar (8-byte) store
+    path and the multi-pass row loop of the writer warps (the reference allows them when CFO compensation does
+    not apply)."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    n_sym, L, syms, start, n_alloc = case
+    if two_hops and len(syms) < 2:
+        if n_sym < 3:
+            pytest.skip("a second hop needs a second pilot symbol")
+        syms2 = [s for s in range(n_sym) if s not in syms][-1:]
+    elif two_hops:
+        syms, syms2 = syms[:1], syms[1:]
+    cfo_comp = n_sym == 14
+    hop1 = synth.make_hop(40, 3, 6, syms, "comb2", (L + 1) // 2, n_sym=n_sym, start_symbol=start, n_alloc=n_alloc)
+    hop2 = synth.make_hop(40, 20, 6, syms2, "comb2", (L + 1) // 2, n_sym=n_sym, start_symbol=start, n_alloc=n_alloc) \
+        if two_hops else synth.no_hop()
+    cfg = synth.make_config(30e3, "filter", cfo_comp)
+    data = synth.make_units(hop1, hop2, cfg, L, 5, pilot_share=1, seed=3, device="cuda")
+    out, sc = estimator.srs_channel_estimator_batched(data["rx"], data["pilots"], 1.0, hop1, hop2, cfg, pilot_share=1)
+    out, sc = out.cpu().numpy(), sc.cpu().numpy()
+    rx, pil = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+    for b in range(5):
+        diag = {}
+        want = ce_oracle.estimate(rx[b], pil[b], 1.0, hop1, hop2, cfg, diagnostics=diag)
+        mx, nmse = tol.grid_errors(out[b], want[0])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (case, two_hops, b, mx, nmse)
+        got = [sc[b, 0], sc[b, 1], sc[b, 2], sc[b, 3], sc[b, 4] if sc[b, 5] else None]
+        tol.check_scalars(got, want[1:], 30e3, diag["ta_margin"], tag=f"{case}/{two_hops}/{b}")
