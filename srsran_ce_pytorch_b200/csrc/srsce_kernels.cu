@@ -827,7 +827,9 @@ KernelFn pick_kernel(const PlanDev& v) {
 int debug_mode() {
   static const int mode = [] {
     const char* e = getenv("SRSCE_DEBUG_ABLATE");
-    return e ? atoi(e) : 0;
+    const int v = e ? atoi(e) : 0;
+    if (v) fprintf(stderr, "libsrsce: SRSCE_DEBUG_ABLATE=%d -- profiling ablation active, RESULTS ARE INVALID\n", v);
+    return v;
   }();
   return mode;
 }

@@ -180,8 +180,10 @@ _PLANS: dict = {}
 _PLANS_LOCK = threading.Lock()
 
 
-def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fill: str = "linear") -> Plan:
-    """Build (or fetch from the cache) the plan for HopConfig x2 + EstimatorConfig + tensor shapes."""
+def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fill: str = "linear",
+              device=None) -> Plan:
+    """Build (or fetch from the cache) the plan for HopConfig x2 + EstimatorConfig + tensor shapes.
+    A plan's tables live on one CUDA device (``device``, default: the current one); the cache is per device."""
     desc = _lib.PlanDesc()
     desc.n_prb_grid, desc.n_sym, desc.n_layers = int(n_prb_grid), int(n_sym), int(n_layers)
     smoothing = getattr(config, "Smoothing", None)
@@ -213,11 +215,21 @@ def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fi
     for g in range(n_cdm):
         desc.re_mask[g] = int(sum(1 << k for k in range(NRE) if rm1[k, g]))
     desc.hop[0], desc.hop[1] = h1, h2
-    key = bytes(desc)
+    if torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    else:
+        dev_index = -1                                  # host-only plan (CPU-side tests of the planner)
+    key = (dev_index, bytes(desc))
     with _PLANS_LOCK:
         plan = _PLANS.get(key)
         if plan is None:
-            plan = _PLANS[key] = Plan(desc)
+            if dev_index >= 0:
+                with torch.cuda.device(dev_index):
+                    plan = Plan(desc)
+            else:
+                plan = Plan(desc)
+            _PLANS[key] = plan
     return plan
 
 
@@ -247,7 +259,8 @@ def srs_channel_estimator_batched(received_rg, pilots, beta_dmrs, hop1, hop2, co
         if pil.shape[0] == 0 or rx.shape[0] % pil.shape[0]:
             raise ValueError("B must be a multiple of the number of pilot blocks")
         pilot_share = rx.shape[0] // pil.shape[0]
-    plan = make_plan(rx.shape[1] // NRE, rx.shape[2], pil.shape[3], hop1, hop2, config, fill)
+    plan = make_plan(rx.shape[1] // NRE, rx.shape[2], pil.shape[3], hop1, hop2, config, fill,
+                     device=rx.device if rx.is_cuda else None)
     return plan.estimate(rx, pil, float(beta_dmrs), pilot_share, out=out, scalars=scalars)
 
 
@@ -263,7 +276,8 @@ def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *,
         raise IndexError("expected received_rg [n_sc, n_sym] and pilots [n_re, n_dmrs, L]")
     if rx.shape[0] % NRE:
         raise IndexError("n_sc must be a multiple of 12")
-    plan = make_plan(rx.shape[0] // NRE, rx.shape[1], pil.shape[2], hop1, hop2, config, fill)
+    plan = make_plan(rx.shape[0] // NRE, rx.shape[1], pil.shape[2], hop1, hop2, config, fill,
+                     device=rx.device if rx.is_cuda else None)
     grid, sc = plan.estimate(rx.unsqueeze(0), pil.unsqueeze(0), float(beta_dmrs), 1)
     cfo = sc[0, 4] if plan.info.cfo_defined else torch.empty((0,), dtype=torch.float64, device=rx.device)
     return grid[0], sc[0, 0], sc[0, 1], sc[0, 2], sc[0, 3], cfo
