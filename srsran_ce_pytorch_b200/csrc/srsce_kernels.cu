@@ -752,6 +752,21 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(0.f, 0.f, 0.f, 0.f));
                 else __stcs(dst, make_float2(0.f, 0.f));
               }
+            } else if (pair && !TWO_HOPS && L == 4 && row_elems == 56 && rows_here == kTileRows) {
+              // the headline shape (4 layers x 14 symbols, full tile, one row per warp pass), fully unrolled with
+              // compile-time strides: one LDS.128 + one STG.128 per row and lane, offsets folded into the instructions
+              const float4* src = reinterpret_cast<const float4*>(tile0 + mine.layer[0]);
+              float4* dst4 = reinterpret_cast<float4*>(dst);
+              const bool on = (mine.flags[0] & 1) != 0;
+#pragma unroll
+              for (int r = 0; r < kTileRows; ++r) {
+                float4 v = on ? src[r * 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_ROT) {
+                  const float2 a = cmul(make_float2(v.x, v.y), mine.rot[0]), b = cmul(make_float2(v.z, v.w), mine.rot[1]);
+                  v = make_float4(a.x, a.y, b.x, b.y);
+                }
+                __stcs(dst4 + r * 28, v);
+              }
             } else if (pair && !TWO_HOPS) {
               // hot loop of the headline configuration: one 16-byte shared load, one 16-byte streaming store
               const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
