@@ -211,6 +211,25 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Writer hot loop for a full 32-row tile of a 14-symbol grid with LL (2 or 4) layers: every lane owns one 16-byte
+// store slot (symbol, layer pair) and walks the rows with compile-time strides, so each row costs one LDS.128 and
+// one STG.128 with the offsets folded into the instructions.  (32 / cols) rows are covered per warp pass.
+template <int LL, bool ROT>
+__device__ __forceinline__ void stream_full_tile(const float4* __restrict__ src, float4* __restrict__ dst, bool on,
+                                                 float2 rot0, float2 rot1) {
+  constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = (kTileRows + kRowsPerPass - 1) / kRowsPerPass;
+  static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    float4 v = on ? src[p * (kRowsPerPass * LL / 2)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ROT) {
+      const float2 a = cmul(make_float2(v.x, v.y), rot0), b = cmul(make_float2(v.z, v.w), rot1);
+      v = make_float4(a.x, a.y, b.x, b.y);
+    }
+    __stcs(dst + p * (kRowsPerPass * kCols), v);
+  }
+}
+
 // Warp-specialised, software-pipelined CTA.  Per unit:
 //   loader   (estimator threads, one unit ahead)  cp.async gather of the pilot REs of the received grid
 //            into ystage[next]; the pilots themselves are warmed in L2
@@ -752,21 +771,12 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 if (VEC == 2) __stcs(reinterpret_cast<float4*>(dst), make_float4(0.f, 0.f, 0.f, 0.f));
                 else __stcs(dst, make_float2(0.f, 0.f));
               }
-            } else if (pair && !TWO_HOPS && L == 4 && row_elems == 56 && rows_here == kTileRows) {
-              // the headline shape (4 layers x 14 symbols, full tile, one row per warp pass), fully unrolled with
-              // compile-time strides: one LDS.128 + one STG.128 per row and lane, offsets folded into the instructions
-              const float4* src = reinterpret_cast<const float4*>(tile0 + mine.layer[0]);
-              float4* dst4 = reinterpret_cast<float4*>(dst);
+            } else if (pair && !TWO_HOPS && rows_here == kTileRows && row_elems == 14 * L && (L == 4 || L == 2)) {
+              // the common shapes (14 symbols x 4 or 2 layers, full tile): fully unrolled with compile-time strides
+              const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
               const bool on = (mine.flags[0] & 1) != 0;
-#pragma unroll
-              for (int r = 0; r < kTileRows; ++r) {
-                float4 v = on ? src[r * 2] : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (HAS_ROT) {
-                  const float2 a = cmul(make_float2(v.x, v.y), mine.rot[0]), b = cmul(make_float2(v.z, v.w), mine.rot[1]);
-                  v = make_float4(a.x, a.y, b.x, b.y);
-                }
-                __stcs(dst4 + r * 28, v);
-              }
+              if (L == 4) stream_full_tile<4, HAS_ROT>(src, reinterpret_cast<float4*>(dst), on, mine.rot[0], mine.rot[1]);
+              else stream_full_tile<2, HAS_ROT>(src, reinterpret_cast<float4*>(dst), on, mine.rot[0], mine.rot[1]);
             } else if (pair && !TWO_HOPS) {
               // hot loop of the headline configuration: one 16-byte shared load, one 16-byte streaming store
               const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
