@@ -76,6 +76,13 @@ CASES = {
     # SNR extremes (noise estimate conditioning) and larger CFO
     "snr0_L2": case(L=2, snr=0.0), "snr40_L2": case(L=2, snr=40.0, cfo_cyc=0.0005),
     "big_cfo_L2": case(L=2, cfo_cyc=0.02),
+    # irregular RE masks (arbitrary 12-bit columns, R not dividing 12, odd pilot counts): the masks the fuzz test draws
+    "irr_R5_L2": case(pat=["110010010100", "001101001010"], L=2, h1=(3, 5, [2, 9])),
+    "irr_R7_L3_2hop": case(pat=["111010100110", "010111010011"], L=3, h1=(1, 3, [4]), h2=(14, [10]), sm="mean"),
+    "irr_R1_off5_L1": case(pat=["000001000000"], L=1, h1=(6, 11, [3, 4])),
+    "irr_R4_L4_none": case(pat=["100100011000", "011000100100"], L=4, h1=(0, 2, [1, 6, 12]), sm="none"),
+    "irr_R2_1prb_L2": case(pat=["010000000010", "000100100000"], L=2, h1=(9, 1, [7])),
+    "irr_R3_L4_alloc": case(pat=["100001000100", "010000100010"], L=4, h1=(2, 7, [5, 8]), start=2, alloc=9, cfo=False),
     # CNN blend switch (ce_dl_cnn CNNSmoothingAlpha)
     "cnn_alpha_0p5_L2": case(L=2, cnn_alpha=0.5), "cnn_alpha_1_comb4_L4": case(L=4, pat="comb4", cnn_alpha=1.0),
 }
@@ -105,6 +112,7 @@ def pack_outputs(tag, out, store):
 
 
 def main():
+    only_new = "--only-new" in sys.argv          # keep the committed fixtures byte for byte, add the missing ones
     sys.path.insert(0, REF_SRC)
     import ce_dl_cnn          # noqa
     import ce_rule_baseline   # noqa
@@ -115,7 +123,9 @@ def main():
     torch.set_num_threads(1)
     total = 0
     for k, (name, c) in enumerate(CASES.items()):
-        hop1, hop2, cfg, rx, pilots, beta = build(name, c, seed=1000 + k)
+        if only_new and (out_dir / f"{name}.npz").exists():
+            continue
+        hop1, hop2, cfg, rx, pilots, beta = build(name, c, seed=1000 + sum(map(ord, name)) if name.startswith("irr_") else 1000 + k)
         store = {
             "rx": rx.numpy(), "pilots": pilots.numpy(), "beta": np.float64(beta),
             "n_layers": np.int64(c["L"]), "scs": np.float64(c["scs"]),
