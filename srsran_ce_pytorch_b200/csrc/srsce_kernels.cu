@@ -1,7 +1,8 @@
 // Fused per-slot port channel estimator for sm_100a.
 //
-// One CTA owns one unit (= one reference call: one received grid, one UE's pilots) at a time and
-// walks the whole reference path without leaving the SM:
+// A persistent, warp-specialised CTA walks units (= reference calls: one received grid, one UE's pilots)
+// through the whole reference path without leaving the SM; its estimator warps run phase A of unit k+1
+// while its writer warps stream phase B of unit k (see the comment above estimate_kernel):
 //
 //   A. gather pilot REs + EPRE + LS de-spreading (y * conj(p))          ce_rule_tensorized.py:571-593
 //      CFO from the first two pilot symbols, de-rotation                :357-451, :596-609
@@ -16,7 +17,7 @@
 //
 // HBM traffic per unit is therefore the algorithmic minimum: pilot REs and pilots read once
 // (the second touch for the noise estimate hits L1/L2), the grid written once.  Phase B is the
-// bandwidth phase (>= 98 % of the bytes); phase A of other resident CTAs overlaps it.
+// bandwidth phase (>= 98 % of the bytes); phase A runs concurrently on the estimator warps.
 //
 // Precision islands follow the reference: complex64 data, float32 |.|^2 partial sums combined in
 // float64, float32 angle; float64 for the virtual-pilot regression, phase unwrap, FIR
@@ -25,8 +26,6 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
-
-#include <mutex>
 
 #include "srsce_internal.h"
 
@@ -868,7 +867,7 @@ std::string cuda_msg(const char* what, cudaError_t e) {
 
 }  // namespace
 
-int max_dynamic_smem() { return 227 * 1024; }
+int max_dynamic_smem() { return 227 * 1024; }   // architectural per-CTA limit on sm_100
 
 int upload_plan(Plan& p, std::string& err) {
   int count = 0;

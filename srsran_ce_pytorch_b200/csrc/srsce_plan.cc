@@ -161,10 +161,8 @@ static void cnn_operator_rows(const std::vector<char>& known, int n_iters, std::
     if (!known[k]) rows[k].swap(lp[k]);
 }
 
-// Pack sparse rows as (first ordinal, T dense coefficients); the first ordinal is pulled back at
-// the band end so that first + T <= n_known and the kernel never has to clamp.
-static int pack_rows(const std::vector<SparseRow>& rows, int n_known, std::vector<int32_t>& idx,
-                     std::vector<float>& coef, int& terms) {
+// Rows are packed as (first ordinal, T dense coefficients): T = widest row span of the operator ...
+static int row_span(const std::vector<SparseRow>& rows) {
   int t_max = 1;
   for (const auto& r : rows) {
     int lo = 1 << 30, hi = -1;
@@ -172,10 +170,10 @@ static int pack_rows(const std::vector<SparseRow>& rows, int n_known, std::vecto
       if (kv.second != 0.0) { lo = std::min(lo, kv.first); hi = std::max(hi, kv.first); }
     if (hi >= 0) t_max = std::max(t_max, hi - lo + 1);
   }
-  terms = std::max(terms, std::min(t_max, n_known));
   return t_max;
 }
 
+// ... and the first ordinal is pulled back at the band end so that first + T <= n_known and the kernel never clamps.
 static void emit_rows(const std::vector<SparseRow>& rows, int n_known, int terms,
                       int32_t* idx, float* coef) {
   for (size_t r = 0; r < rows.size(); ++r) {
@@ -404,9 +402,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
           rows[r][ir] += double(e.alpha);
         }
       }
-      std::vector<int32_t> dummy_i;
-      std::vector<float> dummy_f;
-      pack_rows(rows, N, dummy_i, dummy_f, terms);
+      terms = std::max(terms, std::min(row_span(rows), N));
     }
     if (d.fill == SRSCE_FILL_CNN && terms > kMaxFillTerms)
       FAIL(SRSCE_ERR_UNSUPPORTED, "CNN operator rows span %d pilots (max %d)", terms, kMaxFillTerms);
