@@ -207,6 +207,12 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
+    # Libraries (NCCL's version banner, for one) write to fd 1: keep the process's stdout for the ONE JSON line
+    # and send everything else to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()                     # before CUDA is touched: workers are spawned, not forked
@@ -388,7 +394,8 @@ def run_ours(args):
             line["alt_layout"] = alt
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
