@@ -70,6 +70,8 @@ struct PlanDev {
   int32_t blend;           // CNN blend of the smoothed pilots active (ce_dl_cnn.py:712-717)
   int32_t est_threads;     // NA: 256 (two CTAs per SM) or 512 (one CTA per SM)
   int32_t hall_bufs;       // 1: writers and the next unit's FIR alternate on one pilot buffer; 2: double buffered
+  int32_t y_bufs;          // staging buffers of the received pilot REs: 2 = fetched a whole unit ahead, 1 = during the IFFT
+  int32_t fir_per_group;   // FIR input (ext) holds one CDM group (<= 2 layers) at a time instead of all layers
   // shared-memory carve-up (byte offsets from the dynamic smem base)
   int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
   float cnn_alpha;

@@ -334,12 +334,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
-    const float2* const ys = ystage + (it & 1) * ylen;
+    const float2* const ys = ystage + ((P.y_bufs == 2) ? (it & 1) * ylen : 0);
     const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
     float2* const hall = hall0 + hb_idx * (n_hops * L * N);
     const bool wait_empty = it >= P.hall_bufs;                 // the writers last used this buffer hall_bufs units ago
-    stage_unit(u + gridDim.x, ystage + ((it + 1) & 1) * ylen);
-    cp_async_commit();
+    if (P.y_bufs == 2) {                                       // double buffered: fetch the next unit a whole unit ahead
+      stage_unit(u + gridDim.x, ystage + ((it + 1) & 1) * ylen);
+      cp_async_commit();
+    }
     if (tid < 8) m.acc[tid] = 0.0;
     // (visibility of m.acc is ordered by the barriers below)
 
@@ -394,24 +396,29 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         sync_a<NA>();
       }
 
-      // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584)
+      // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584), then smoothing
+      //      (:633-668).  With the raised-cosine filter the raw pilots go through ext (FIR input); when the
+      //      planner asked for it, one CDM group (<= 2 layers) at a time so that ext stays small.
       float epre_part = 0.f;
       if (!filt && hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // LS writes hall: writers must be done with it
-      {
-        float2* const dst = filt ? ext + pad + nv : hbuf;
-        const int dstride = filt ? EF : N;
-        if (filt) {                                  // zero margins of the FIR input
-          for (int k = tid; k < 2 * pad * L; k += kThreads) {
-            const int l = k / (2 * pad), j = k - l * 2 * pad;
-            ext[l * EF + (j < pad ? j : EF - 2 * pad + j)] = make_float2(0.f, 0.f);
+      const int n_batches = (filt && P.fir_per_group) ? G : 1;
+      for (int bt = 0; bt < n_batches; ++bt) {
+        const int g_lo = (n_batches == 1) ? 0 : bt, g_hi = (n_batches == 1) ? G : bt + 1;
+        const int l_lo = 2 * g_lo, LB = min(L, 2 * g_hi) - l_lo;          // layers of this batch: l_lo .. l_lo + LB - 1
+        {
+          float2* const dst = filt ? ext + pad + nv : hbuf;               // filt: layer index relative to the batch
+          const int dstride = filt ? EF : N;
+          if (filt) {                                  // zero margins of the FIR input
+            for (int k = tid; k < 2 * pad * LB; k += kThreads) {
+              const int l = k / (2 * pad), j = k - l * 2 * pad;
+              ext[l * EF + (j < pad ? j : EF - 2 * pad + j)] = make_float2(0.f, 0.f);
+            }
           }
-        }
-        const float inv_s = 1.0f / float(S);
-        const int n_pairs = (N + 1) >> 1;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g < G) {
+          const float inv_s = 1.0f / float(S);
+          const int n_pairs = (N + 1) >> 1;
+          for (int g = g_lo; g < g_hi; ++g) {
             const bool two = 2 * g + 1 < L;
+            const int lrel = filt ? 2 * g - l_lo : 2 * g;
             for (int pr = tid; pr < n_pairs; pr += kThreads) {
               float2 h[2][2];
 #pragma unroll
@@ -446,17 +453,78 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               for (int e = 0; e < 2; ++e) {
                 const int i = i0 + e;
                 if (i < N) {
-                  dst[2 * g * dstride + i] = h[e][0];
-                  if (two) dst[(2 * g + 1) * dstride + i] = h[e][1];
+                  dst[lrel * dstride + i] = h[e][0];
+                  if (two) dst[(lrel + 1) * dstride + i] = h[e][1];
                 }
               }
             }
           }
         }
-      }
-      sync_a<NA>();
+        sync_a<NA>();
 
-      // ---- smoothing (:633-668)
+        if (filt) {
+          if (nv > 0) {
+            // one thread per (layer, edge, pilot): modulus / phase first, then every thread fits the two
+            // lines of its edge and evaluates its own virtual pilot
+            const int l = tid / (2 * nv), r = tid - l * 2 * nv, end = r / nv, k = r - end * nv;
+            float2* const x = ext + l * EF + pad;              // x[0..nv) virtual | x[nv..nv+N) real | virtual
+            if (tid < 2 * LB * nv) {
+              const float2 e = end ? x[nv + N - 1 - k] : x[nv + k];
+              m.vp_mod[l][end][k] = sqrtf(e.x * e.x + e.y * e.y);
+              m.vp_ph[l][end][k] = atan2f(e.y, e.x);
+            }
+            sync_a<NA>();
+            if (tid < 2 * LB * nv) {
+              const float2 val = virtual_pilot(nv, P.vp_mx, P.vp_den, m.vp_mod[l][end], m.vp_ph[l][end], k);
+              if (end) x[nv + N + (nv - 1 - k)] = val;
+              else x[k] = val;
+            }
+          }
+          sync_a<NA>();
+          if (hh == 0 && bt == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
+          // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493);
+          // two adjacent outputs per thread share all but one of their input samples
+          for (int l = 0; l < LB; ++l) {
+            const float2* const xl = ext + l * EF + nv + 2 * pad;    // tap k of output i multiplies xl[i - k]
+            float2* const hl = hbuf + (l_lo + l) * N;
+            for (int i = 2 * tid; i < N; i += 2 * kThreads) {
+              double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+              const float2 t1 = (i + 1 < N) ? xl[i + 1] : make_float2(0.f, 0.f);
+              double tx1 = double(t1.x), ty1 = double(t1.y);
+              for (int k = 0; k < K; ++k) {
+                const float2 t0 = xl[i - k];
+                const double tx0 = double(t0.x), ty0 = double(t0.y), w = m.taps[k];
+                ar0 += w * tx0;
+                ai0 += w * ty0;
+                ar1 += w * tx1;
+                ai1 += w * ty1;
+                tx1 = tx0;
+                ty1 = ty0;
+              }
+              hl[i] = make_float2(float(ar0), float(ai0));
+              if (i + 1 < N) hl[i + 1] = make_float2(float(ar1), float(ai1));
+            }
+          }
+          sync_a<NA>();
+          if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
+            float2* const hb0 = hbuf + l_lo * N;
+            for (int idx = tid; idx < N * LB; idx += kThreads) {
+              const int l = idx / N, i = idx - l * N;
+              const int il = (i == 0) ? 1 : i - 1, ir = (i == N - 1) ? N - 2 : i + 1;
+              const float2 a = hb0[l * N + il], b = hb0[idx], c = hb0[l * N + ir];
+              ext[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
+                                     float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
+            }
+            sync_a<NA>();
+            for (int idx = tid; idx < N * LB; idx += kThreads) {
+              const float2 s0 = hb0[idx], lp = ext[idx];
+              hb0[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
+            }
+            sync_a<NA>();
+          }
+        }
+      }  // group batches
+
       if (P.smoothing == SRSCE_SMOOTH_MEAN) {
         double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
@@ -479,65 +547,6 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           hbuf[idx] = make_float2(float(m.tot[2 * l]) * inv_n, float(m.tot[2 * l + 1]) * inv_n);
         }
         sync_a<NA>();
-      } else if (P.smoothing == SRSCE_SMOOTH_FILTER) {
-        if (nv > 0) {
-          // one thread per (layer, edge, pilot): modulus / phase first, then every thread fits the two
-          // lines of its edge and evaluates its own virtual pilot
-          const int l = tid / (2 * nv), r = tid - l * 2 * nv, end = r / nv, k = r - end * nv;
-          float2* const x = ext + l * EF + pad;              // x[0..nv) virtual | x[nv..nv+N) real | virtual
-          if (tid < 2 * L * nv) {
-            const float2 e = end ? x[nv + N - 1 - k] : x[nv + k];
-            m.vp_mod[l][end][k] = sqrtf(e.x * e.x + e.y * e.y);
-            m.vp_ph[l][end][k] = atan2f(e.y, e.x);
-          }
-          sync_a<NA>();
-          if (tid < 2 * L * nv) {
-            const float2 val = virtual_pilot(nv, P.vp_mx, P.vp_den, m.vp_mod[l][end], m.vp_ph[l][end], k);
-            if (end) x[nv + N + (nv - 1 - k)] = val;
-            else x[k] = val;
-          }
-        }
-        sync_a<NA>();
-        if (hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
-        // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493)
-        // two adjacent outputs per thread share all but one of their input samples
-        for (int l = 0; l < L; ++l) {
-          const float2* const xl = ext + l * EF + nv + 2 * pad;    // tap k of output i multiplies xl[i - k]
-          float2* const hl = hbuf + l * N;
-          for (int i = 2 * tid; i < N; i += 2 * kThreads) {
-            double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
-            const float2 t1 = (i + 1 < N) ? xl[i + 1] : make_float2(0.f, 0.f);
-            double tx1 = double(t1.x), ty1 = double(t1.y);
-            for (int k = 0; k < K; ++k) {
-              const float2 t0 = xl[i - k];
-              const double tx0 = double(t0.x), ty0 = double(t0.y), w = m.taps[k];
-              ar0 += w * tx0;
-              ai0 += w * ty0;
-              ar1 += w * tx1;
-              ai1 += w * ty1;
-              tx1 = tx0;
-              ty1 = ty0;
-            }
-            hl[i] = make_float2(float(ar0), float(ai0));
-            if (i + 1 < N) hl[i + 1] = make_float2(float(ar1), float(ai1));
-          }
-        }
-        sync_a<NA>();
-        if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
-          for (int idx = tid; idx < N * L; idx += kThreads) {
-            const int l = idx / N, i = idx - l * N;
-            const int il = (i == 0) ? 1 : i - 1, ir = (i == N - 1) ? N - 2 : i + 1;
-            const float2 a = hbuf[l * N + il], b = hbuf[idx], c = hbuf[l * N + ir];
-            ext[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
-                                   float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
-          }
-          sync_a<NA>();
-          for (int idx = tid; idx < N * L; idx += kThreads) {
-            const float2 s0 = hbuf[idx], lp = ext[idx];
-            hbuf[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
-          }
-          sync_a<NA>();
-        }
       }
 
       // ---- the smoothed pilots of every hop are final: build the store-slot table (final CFO
@@ -547,6 +556,46 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         build_store_table(m.col[hb_idx]);
         write_symbol_rotation(u);
         bar_arrive(kBarFull + hb_idx, kCtaThreads);
+      }
+
+      // ---- reconstruction, noise, RSRP (:701-730)
+      {
+        float noise_part = 0.f, rsrp_part = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g < G) {
+            const bool two = 2 * g + 1 < L;
+            for (int i = tid; i < N; i += kThreads) {
+              const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
+              const float2* yp = yh + (g * N + i) * S;
+              const float2 h0 = hbuf[2 * g * N + i];
+              const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
+              for (int s = 0; s < S; ++s) {
+                const float2 y = yp[s];
+                float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, m.rot_pos[s]) : h0);
+                if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, m.rot_pos[s]) : h1));
+                const float2 d = csub(y, cscale(e, beta));
+                noise_part += d.x * d.x + d.y * d.y;
+              }
+            }
+          }
+        }
+        for (int idx = tid; idx < N * L; idx += kThreads) {
+          const float2 t = hbuf[idx];
+          rsrp_part += t.x * t.x + t.y * t.y;
+        }
+        double v[3] = {double(epre_part), double(noise_part), double(rsrp_part)};
+        block_sum<NA, 3>(m, v);
+        if (tid == 0) {
+          m.acc[0] += double(float(m.tot[0]));
+          m.acc[1] += double(float(m.tot[1]));
+          m.acc[2] += beta_d * beta_d * double(float(m.tot[2])) * double(S);
+        }
+      }
+      sync_a<NA>();
+      if (P.y_bufs == 1 && hh == n_hops - 1) {                  // single staging buffer: this unit's pilot REs are dead now;
+        stage_unit(u + gridDim.x, ystage);                     // the next unit's arrive while the IFFT below runs
+        cp_async_commit();
       }
 
       // ---- time alignment (:674-698)
@@ -605,42 +654,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
         }
       }
-
-      // ---- reconstruction, noise, RSRP (:701-730)
-      {
-        float noise_part = 0.f, rsrp_part = 0.f;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g < G) {
-            const bool two = 2 * g + 1 < L;
-            for (int i = tid; i < N; i += kThreads) {
-              const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
-              const float2* yp = yh + (g * N + i) * S;
-              const float2 h0 = hbuf[2 * g * N + i];
-              const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
-              for (int s = 0; s < S; ++s) {
-                const float2 y = yp[s];
-                float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, m.rot_pos[s]) : h0);
-                if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, m.rot_pos[s]) : h1));
-                const float2 d = csub(y, cscale(e, beta));
-                noise_part += d.x * d.x + d.y * d.y;
-              }
-            }
-          }
-        }
-        for (int idx = tid; idx < N * L; idx += kThreads) {
-          const float2 t = hbuf[idx];
-          rsrp_part += t.x * t.x + t.y * t.y;
-        }
-        double v[3] = {double(epre_part), double(noise_part), double(rsrp_part)};
-        block_sum<NA, 3>(m, v);
-        if (tid == 0) {
-          m.acc[0] += double(float(m.tot[0]));
-          m.acc[1] += double(float(m.tot[1]));
-          m.acc[2] += beta_d * beta_d * double(float(m.tot[2])) * double(S);
-        }
-      }
-      sync_a<NA>();
+      sync_a<NA>();   // ext (IFFT scratch) and the profile are rewritten by the next hop / unit
     }  // hops
 
     if (dbg & 1) {                                            // profiling ablation: writers run on stale pilots

@@ -437,35 +437,49 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     }
   }
 
-  // shared memory: smoothed pilots of every hop | staged pilot REs of this and the next unit |
-  // raw pilots + virtual pilots, later FFT scratch | the writer warps' expansion tiles | small tables
+  // shared memory: smoothed pilots of every hop (x hall_bufs) | staged pilot REs (x y_bufs) | raw pilots +
+  // virtual pilots, later FFT scratch | the writer warps' expansion tiles | small tables.
+  // The planner walks a short list of layouts and takes the first that fits its budget:
+  //   A  two CTAs of 256 estimator threads (+6 writer warps) per SM, pilot REs fetched a whole unit ahead.  The
+  //      two-CTA footprint is held under the 196 KB carve-out (1 KB per CTA is reserved by the system): one
+  //      step higher leaves 28 KB instead of 60 KB of L1 for phase A's twiddle / pilot loads, measured to cost
+  //      11 % of the headline throughput.
+  //   B  the same CTA shape with a slimmer footprint: one staging buffer (the next unit's pilot REs are fetched
+  //      while the IFFT runs), FIR input one CDM group at a time, IFFT two layers at a time.
+  //   C  one CTA of 512 estimator threads (+8 writer warps), slim footprint, pilot REs fetched a whole unit ahead.
+  //   D  the same with one staging buffer (the largest geometries).
+  //   (Double buffering the smoothed pilots of a lone CTA was measured slower on B200 in every variant tried.)
   {
     const int h_elems = n_hops * N * L;
-    const int y_elems = 2 * G * N * s_total;
-    int ext = (N + 2 * v.n_virtual + 2 * (v.n_taps / 2)) * L;      // FIR input incl. virtual pilots and zero margins
-    ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
-    ext = std::max(ext, N * L);                                   // scratch of the CNN blend
+    const int y_unit = G * N * s_total;
+    const int fir_len = N + 2 * v.n_virtual + 2 * (v.n_taps / 2);
+    const int fft_default = std::max(1, std::min(L, 4096 / v.fft_size));
     auto up16 = [](int bytes) { return ((bytes + 15) / 16) * 16; };
-    v.ext_elems = ext;
-    // Two CTAs of 256 estimator threads (+6 writer warps) per SM when they fit, else one CTA of 512 (+8).
-    // The two-CTA footprint is held under the 196 KB shared-memory carve-out (1 KB per CTA is reserved by
-    // the system): one step higher leaves 28 KB instead of 60 KB of L1 for the twiddle / pilot loads of
-    // phase A, which was measured to cost 11 % of the headline throughput.
-    auto layout = [&](int na, int bufs) {
+    auto layout = [&](int na, int hall_bufs, int y_bufs, bool slim) {
+      const int ext_layers = slim ? std::min(L, 2) : L;
+      v.fir_per_group = (slim && L > 2) ? 1 : 0;
+      v.fft_layers = slim ? std::min(fft_default, 2) : fft_default;
+      int ext = fir_len * ext_layers;                                // FIR input incl. virtual pilots and zero margins
+      ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
+      ext = std::max(ext, N * ext_layers);                          // scratch of the CNN blend
       const int tile_elems = writer_warps(na) * kTileRows * L * n_hops;
+      v.ext_elems = ext;
       v.est_threads = na;
-      v.hall_bufs = bufs;
+      v.hall_bufs = hall_bufs;
+      v.y_bufs = y_bufs;
       v.off_h = 0;
-      v.off_y = v.off_h + up16(bufs * h_elems * 8);
-      v.off_ext = v.off_y + up16(y_elems * 8);
+      v.off_y = v.off_h + up16(hall_bufs * h_elems * 8);
+      v.off_ext = v.off_y + up16(y_bufs * y_unit * 8);
       v.off_tile = v.off_ext + up16(ext * 8);
       v.off_misc = v.off_tile + up16(tile_elems * 8);
       v.smem_bytes = v.off_misc + kMiscBytes;
+      return v.smem_bytes;
     };
-    layout(256, 1);
-    if (2 * (v.smem_bytes + 1024) > 196 * 1024) layout(512, 1);
-    // (double buffering the smoothed pilots of a single resident CTA -- layout(512, 2) -- was measured
-    //  slower on B200: the larger carve-out leaves less L1 for phase A's pilot / twiddle loads)
+    const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
+    (void)one_cta_l1_budget;
+    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
+        layout(512, 1, 2, true) > 227 * 1024)
+      layout(512, 1, 1, true);
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }
