@@ -12,6 +12,8 @@
 //   ce_dl_cnn inpainting + low-pass         ce_dl_cnn.py:433-508, :274-295
 //   final normalisation                     ce_rule_tensorized.py:899-919
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -446,9 +448,10 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   //      11 % of the headline throughput.
   //   B  the same CTA shape with a slimmer footprint: one staging buffer (the next unit's pilot REs are fetched
   //      while the IFFT runs), FIR input one CDM group at a time, IFFT two layers at a time.
-  //   C  one CTA of 512 estimator threads (+8 writer warps), slim footprint, pilot REs fetched a whole unit ahead.
-  //   D  the same with one staging buffer (the largest geometries).
-  //   (Double buffering the smoothed pilots of a lone CTA was measured slower on B200 in every variant tried.)
+  //   C  one CTA of 512 estimator threads (+8 writer warps) with the slim footprint.
+  //   Measured on B200 (comb-2, 273 PRB): the smaller the footprint, the faster -- phase A re-reads the pilots
+  //   through L1, and L1 is what shared memory leaves over: 127 KB 0.59, 153 KB 0.57, 174 KB 0.58, 180 KB 0.54,
+  //   206 KB (smoothed pilots double buffered) 0.50 of the HBM peak.
   {
     const int h_elems = n_hops * N * L;
     const int y_unit = G * N * s_total;
@@ -477,9 +480,11 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     };
     const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
     (void)one_cta_l1_budget;
-    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
-        layout(512, 1, 2, true) > 227 * 1024)
-      layout(512, 1, 1, true);
+    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget) layout(512, 1, 1, true);
+    if (const char* e = getenv("SRSCE_DEBUG_LAYOUT")) {       // experiments only: "na,hall_bufs,y_bufs,slim"
+      int na = 256, hb = 1, yb = 2, sl = 0;
+      if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512)) layout(na, hb, yb, sl != 0);
+    }
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }
