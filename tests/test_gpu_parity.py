@@ -251,3 +251,32 @@ def test_short_and_odd_grids_match_oracle(case, two_hops):
         assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (case, two_hops, b, mx, nmse)
         got = [sc[b, 0], sc[b, 1], sc[b, 2], sc[b, 3], sc[b, 4] if sc[b, 5] else None]
         tol.check_scalars(got, want[1:], 30e3, diag["ta_margin"], tag=f"{case}/{two_hops}/{b}")
+
+
+@pytest.mark.parametrize("pattern,syms,n_units", [("comb4", [3, 10], 720), ("comb2", [13], 400), ("comb2", [3, 10], 330),
+                                                   ("type2", [6], 640), ("comb4", [2, 5, 8, 11], 340)],
+                         ids=["slim-2cta-S2", "one-cta-comb2", "one-cta-comb2-S2", "slim-type2", "one-cta-S4"])
+def test_persistent_loop_full_band_layouts(pattern, syms, n_units):
+    """Full-band geometries that select the other shared-memory layouts (single staging buffer, per-group FIR
+    input, one 768-thread CTA per SM), with more units than resident CTAs so that every CTA pipelines several."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    hop1 = synth.make_hop(273, 0, 273, syms, pattern, 2)
+    cfg = synth.make_config(30e3, "filter", True)
+    gen = 20
+    data = synth.make_units(hop1, synth.no_hop(), cfg, 4, gen, pilot_share=4, seed=21, device="cuda")
+    reps = n_units // gen
+    rx, pil = data["rx"].repeat(reps, 1, 1), data["pilots"].repeat(reps, 1, 1, 1)
+    out, sc = estimator.srs_channel_estimator_batched(rx, pil, 1.0, hop1, synth.no_hop(), cfg, pilot_share=4)
+    # every repetition of the 20 generated units must be bit-identical, wherever in the launch it was processed
+    ref_out, ref_sc = out[:gen], sc[:gen]
+    for r in (1, reps // 2, reps - 1):
+        assert torch.equal(out[r * gen:(r + 1) * gen], ref_out) and torch.equal(sc[r * gen:(r + 1) * gen], ref_sc), r
+    rx_h, pil_h = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+    for b in (0, 7, 19):
+        diag = {}
+        want = ce_oracle.estimate(rx_h[b], pil_h[b // 4], 1.0, hop1, synth.no_hop(), cfg, diagnostics=diag)
+        mx, nmse = tol.grid_errors(out[(reps - 1) * gen + b].cpu().numpy(), want[0])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (pattern, syms, b, mx, nmse)
+        s = sc[(reps - 1) * gen + b].cpu().numpy()
+        tol.check_scalars([s[0], s[1], s[2], s[3], s[4] if s[5] else None], want[1:], 30e3, diag["ta_margin"],
+                          tag=f"layouts/{pattern}/{b}")
