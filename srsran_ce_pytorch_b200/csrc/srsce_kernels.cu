@@ -229,6 +229,28 @@ __device__ __forceinline__ void stream_full_tile(const float4* __restrict__ src,
   }
 }
 
+// The same for two hops: rows inside hop 2's band take hop 2's value on the symbols of hop 2's allocation
+// (it wins where the hops overlap), otherwise hop 1's on hop 1's allocated symbols, otherwise zero.
+template <int LL, bool ROT>
+__device__ __forceinline__ void stream_full_tile_2hop(const float4* __restrict__ src1, const float4* __restrict__ src2,
+                                                      float4* __restrict__ dst, int flags, unsigned in1, unsigned in2,
+                                                      int first_row, float2 rot0, float2 rot1) {
+  constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = kTileRows / kRowsPerPass;
+  const unsigned use1 = (flags & 1) ? (in1 >> first_row) : 0u, use2 = (flags & 2) ? (in2 >> first_row) : 0u;
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    const int r = p * kRowsPerPass;                      // row of this lane = first_row + r
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((use2 >> r) & 1u) v = src2[p * (kRowsPerPass * LL / 2)];
+    else if ((use1 >> r) & 1u) v = src1[p * (kRowsPerPass * LL / 2)];
+    if (ROT) {
+      const float2 a = cmul(make_float2(v.x, v.y), rot0), b = cmul(make_float2(v.z, v.w), rot1);
+      v = make_float4(a.x, a.y, b.x, b.y);
+    }
+    __stcs(dst + p * (kRowsPerPass * kCols), v);
+  }
+}
+
 // Warp-specialised, software-pipelined CTA.  Per unit:
 //   loader   (estimator threads, one unit ahead)  cp.async gather of the pilot REs of the received grid
 //            into ystage[next]; the pilots themselves are warmed in L2
@@ -790,6 +812,15 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               const bool on = (mine.flags[0] & 1) != 0;
               if (L == 4) stream_full_tile<4, HAS_ROT>(src, reinterpret_cast<float4*>(dst), on, mine.rot[0], mine.rot[1]);
               else stream_full_tile<2, HAS_ROT>(src, reinterpret_cast<float4*>(dst), on, mine.rot[0], mine.rot[1]);
+            } else if (pair && TWO_HOPS && rows_here == kTileRows && row_elems == 14 * L && (L == 4 || L == 2)) {
+              const float4* s1 = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
+              const float4* s2 = s1 + kTileRows * L / 2;
+              if (L == 4)
+                stream_full_tile_2hop<4, HAS_ROT>(s1, s2, reinterpret_cast<float4*>(dst), mine.flags[0], in1, in2, my_rs,
+                                                  mine.rot[0], mine.rot[1]);
+              else
+                stream_full_tile_2hop<2, HAS_ROT>(s1, s2, reinterpret_cast<float4*>(dst), mine.flags[0], in1, in2, my_rs,
+                                                  mine.rot[0], mine.rot[1]);
             } else if (pair && !TWO_HOPS) {
               // hot loop of the headline configuration: one 16-byte shared load, one 16-byte streaming store
               const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);

@@ -119,3 +119,32 @@ def test_no_cpu_fallback():
         strides = (C.c_int64 * 3)(1, 1, 1)
         rc = _lib.lib.srsce_estimate(plan._h, 16, strides, 16, 1, 1.0, 16, 16, 1, None)
         assert rc == _lib.ERR_NO_DEVICE and "no CPU compute path" in _lib.last_error()
+
+
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(bits0=st.integers(1, 4095), n_prbs=st.integers(1, 9), shift=st.integers(0, 11), fill=st.sampled_from(["linear", "cnn"]))
+def test_fill_operator_property_random_masks(bits0, n_prbs, shift, fill):
+    """Any 12-bit RE mask (second CDM group = a rotation of the first, so both select the same number of REs):
+    the planner's operator rows reproduce the oracle's fill of random pilots."""
+    col0 = "".join("1" if (bits0 >> k) & 1 else "0" for k in range(12))
+    col1 = col0[shift:] + col0[:shift]
+    hop1 = synth.make_hop(30, 2, n_prbs, [3], [col0, col1], 2)
+    cfg = synth.make_config(30e3, "none", False)
+    try:
+        plan = estimator.make_plan(30, 14, 4, hop1, synth.no_hop(), cfg, fill)
+    except NotImplementedError:
+        return                                              # operator wider than the kernel's row budget: refused, not wrong
+    _, idx, coef = plan.tables()
+    spec = ce_oracle.hop_from_any(hop1)
+    n = plan.info.n_re
+    rng = np.random.default_rng(bits0)
+    for g in range(2):
+        h = (rng.standard_normal((n, 2)) + 1j * rng.standard_normal((n, 2))).astype(np.complex64)
+        want = ce_oracle._fill_band(h, spec, g, "cnn" if fill == "cnn" else "tensorized")
+        got = np.zeros_like(want, dtype=np.complex128)
+        for t in range(coef.shape[2]):
+            got += coef[g, :, t, None].astype(np.float64) * h[np.minimum(idx[g] + t, n - 1)].astype(np.complex128)
+        assert np.abs(got - want).max() <= 3e-6 * max(np.abs(want).max(), 1e-30)
