@@ -229,6 +229,26 @@ __device__ __forceinline__ void stream_full_tile(const float4* __restrict__ src,
   }
 }
 
+// Odd layer counts (1 or 3): the two complex64 elements of a 16-byte slot belong to different (symbol, layer)
+// pairs, so each is fetched (8 bytes) and gated on its own; strides are still compile-time constants.
+template <int LL, bool ROT>
+__device__ __forceinline__ void stream_full_tile_odd(const float2* __restrict__ src0, const float2* __restrict__ src1,
+                                                     float4* __restrict__ dst, bool on0, bool on1, float2 rot0,
+                                                     float2 rot1) {
+  constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = kTileRows / kRowsPerPass;
+  static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
+#pragma unroll
+  for (int p = 0; p < kPasses; ++p) {
+    float2 a = on0 ? src0[p * (kRowsPerPass * LL)] : make_float2(0.f, 0.f);
+    float2 b = on1 ? src1[p * (kRowsPerPass * LL)] : make_float2(0.f, 0.f);
+    if (ROT) {
+      a = cmul(a, rot0);
+      b = cmul(b, rot1);
+    }
+    __stcs(dst + p * (kRowsPerPass * kCols), make_float4(a.x, a.y, b.x, b.y));
+  }
+}
+
 // The same for two hops: rows inside hop 2's band take hop 2's value on the symbols of hop 2's allocation
 // (it wins where the hops overlap), otherwise hop 1's on hop 1's allocated symbols, otherwise zero.
 template <int LL, bool ROT>
@@ -821,6 +841,12 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               else
                 stream_full_tile_2hop<2, HAS_ROT>(s1, s2, reinterpret_cast<float4*>(dst), mine.flags[0], in1, in2, my_rs,
                                                   mine.rot[0], mine.rot[1]);
+            } else if (VEC == 2 && !TWO_HOPS && rows_here == kTileRows && row_elems == 14 * L && (L == 1 || L == 3)) {
+              const float2* s0 = tile0 + my_rs * L + mine.layer[0];
+              const float2* s1 = tile0 + my_rs * L + mine.layer[1];
+              const bool on0 = (mine.flags[0] & 1) != 0, on1 = (mine.flags[1] & 1) != 0;
+              if (L == 1) stream_full_tile_odd<1, HAS_ROT>(s0, s1, reinterpret_cast<float4*>(dst), on0, on1, mine.rot[0], mine.rot[1]);
+              else stream_full_tile_odd<3, HAS_ROT>(s0, s1, reinterpret_cast<float4*>(dst), on0, on1, mine.rot[0], mine.rot[1]);
             } else if (pair && !TWO_HOPS) {
               // hot loop of the headline configuration: one 16-byte shared load, one 16-byte streaming store
               const float4* src = reinterpret_cast<const float4*>(tile0 + my_rs * L + mine.layer[0]);
