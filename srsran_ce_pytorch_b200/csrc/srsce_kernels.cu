@@ -44,19 +44,23 @@ struct Misc {
   double red[kMaxWarpsA][8];
   double tot[8];
   double acc[8];           // 0 epre, 1 noise, 2 rsrp, 3 ta, 4 cfo, 5 cfo defined
+  double ta_hop[2];
   double taps[SRSCE_MAX_TAPS + 1];
-  float2 rot_neg[SRSCE_MAX_SYMBOLS];
-  float2 rot_pos[SRSCE_MAX_SYMBOLS];
-  float prof[2 * SRSCE_TA_WINDOW];
   LerpEntry lerp[2][kNRE];
   int32_t re_pos[2][kNRE];
   unsigned long long r_magic;
   float cnn_coef[2][kNRE][kMaxFillTerms];
   int32_t cnn_idx0[2][kNRE];
-  float vp_mod[SRSCE_MAX_LAYERS][2][12];   // modulus / phase of the edge pilots (virtual-pilot regression)
-  float vp_ph[SRSCE_MAX_LAYERS][2][12];
   ColInfo col[2][SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];   // one store-slot table per hall buffer
 };
+struct HopScratch {        // per hop, after Misc
+  float2 rot_neg[SRSCE_MAX_SYMBOLS];
+  float2 rot_pos[SRSCE_MAX_SYMBOLS];
+  float prof[2 * SRSCE_TA_WINDOW];
+  float vp_mod[SRSCE_MAX_LAYERS][2][12];   // modulus / phase of the edge pilots (virtual-pilot regression)
+  float vp_ph[SRSCE_MAX_LAYERS][2][12];
+};
+static_assert(sizeof(HopScratch) <= kHopScratchBytes, "HopScratch does not fit its shared-memory slot");
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -298,6 +302,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   float2* const tiles = reinterpret_cast<float2*>(smem + P.off_tile);
   float2* const ext = reinterpret_cast<float2*>(smem + P.off_ext);
   Misc& m = *reinterpret_cast<Misc*>(smem + P.off_misc);
+  HopScratch* const hsx = reinterpret_cast<HopScratch*>(smem + P.off_misc + kMiscBytes);   // [n_hops]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = P.n_layers, G = P.n_cdm, R = P.re_per_prb, N = P.n_re, ST = P.n_dmrs_total;
@@ -388,16 +393,16 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     // (visibility of m.acc is ordered by the barriers below)
 
     // ===================================== phase A ==========================================
-    for (int hh = 0; hh < ((dbg & 1) ? 0 : n_hops); ++hh) {
-      const HopDev& H = P.hop[hh];
-      const int S = H.n_dmrs, col0 = H.pilot_col0;
-      float2* const hbuf = hall + hh * L * N;
-      const float2* const yh = ys + G * N * col0;             // [group][pilot][symbol] of this hop
-      const bool est_cfo = S >= 2;
-      const bool derot = est_cfo && P.cfo_compensate;
-
-      // ---- CFO: correlate the first two pilot symbols (compensate_cfo :357-451)
-      if (est_cfo) {
+    // Step major: every step handles both hops before the next barrier, so that a two-hop unit pays the
+    // barrier / latency chain of phase A once, not twice.
+    if (!(dbg & 1)) {
+      // ---- CFO: correlate the first two pilot symbols of each hop (compensate_cfo :357-451)
+#pragma unroll
+      for (int hh = 0; hh < n_hops; ++hh) {
+        const HopDev& H = P.hop[hh];
+        const int S = H.n_dmrs, col0 = H.pilot_col0;
+        if (S < 2) continue;
+        const float2* const yh = ys + G * N * col0;           // [group][pilot][symbol] of this hop
         float2 c[2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -428,32 +433,39 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           const double cfo_hop = tot / H.cfo_den;
           m.acc[4] = (m.acc[5] != 0.0) ? 0.5 * (m.acc[4] + cfo_hop) : cfo_hop;   // :605-609
           m.acc[5] = 1.0;
+          const bool derot = P.cfo_compensate != 0;
           for (int s = 0; s < S; ++s) {
             double sn = 0.0, cs = 1.0;
             if (derot) sincos(2.0 * M_PI * H.t_dmrs[s] * cfo_hop, &sn, &cs);
-            m.rot_pos[s] = make_float2(float(cs), float(sn));
-            m.rot_neg[s] = make_float2(float(cs), float(-sn));
+            hsx[hh].rot_pos[s] = make_float2(float(cs), float(sn));
+            hsx[hh].rot_neg[s] = make_float2(float(cs), float(-sn));
           }
         }
-        sync_a<NA>();
       }
+      if (P.cfo_defined) sync_a<NA>();
 
       // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584), then smoothing
-      //      (:633-668).  With the raised-cosine filter the raw pilots go through ext (FIR input); when the
-      //      planner asked for it, one CDM group (<= 2 layers) at a time so that ext stays small.
-      float epre_part = 0.f;
-      if (!filt && hh == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // LS writes hall: writers must be done with it
+      //      (:633-668).  With the raised-cosine filter the raw pilots go through ext (FIR input, one region
+      //      per hop); when the planner asked for it, one CDM group (<= 2 layers) at a time so that ext stays small.
+      float epre_part[2] = {0.f, 0.f};
+      if (!filt && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // LS writes hall: writers must be done with it
       const int n_batches = (filt && P.fir_per_group) ? G : 1;
       for (int bt = 0; bt < n_batches; ++bt) {
         const int g_lo = (n_batches == 1) ? 0 : bt, g_hi = (n_batches == 1) ? G : bt + 1;
         const int l_lo = 2 * g_lo, LB = min(L, 2 * g_hi) - l_lo;          // layers of this batch: l_lo .. l_lo + LB - 1
-        {
-          float2* const dst = filt ? ext + pad + nv : hbuf;               // filt: layer index relative to the batch
+#pragma unroll
+        for (int hh = 0; hh < n_hops; ++hh) {
+          const HopDev& H = P.hop[hh];
+          const int S = H.n_dmrs, col0 = H.pilot_col0;
+          const bool derot = S >= 2 && P.cfo_compensate;
+          const float2* const yh = ys + G * N * col0;
+          float2* const exth = ext + hh * P.ext_hop;
+          float2* const dst = filt ? exth + pad + nv : hall + hh * L * N;   // filt: layer index relative to the batch
           const int dstride = filt ? EF : N;
           if (filt) {                                  // zero margins of the FIR input
             for (int k = tid; k < 2 * pad * LB; k += kThreads) {
               const int l = k / (2 * pad), j = k - l * 2 * pad;
-              ext[l * EF + (j < pad ? j : EF - 2 * pad + j)] = make_float2(0.f, 0.f);
+              exth[l * EF + (j < pad ? j : EF - 2 * pad + j)] = make_float2(0.f, 0.f);
             }
           }
           const float inv_s = 1.0f / float(S);
@@ -472,13 +484,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                   const float2* yp = yh + (g * N + i) * S;
                   for (int s = 0; s < S; ++s) {
                     const float2 y = yp[s];
-                    epre_part += y.x * y.x + y.y * y.y;
+                    epre_part[hh] += y.x * y.x + y.y * y.y;
                     float2 x0 = cmul_conj(y, __ldg(pp + s * L));
-                    if (derot) x0 = cmul(x0, m.rot_neg[s]);
+                    if (derot) x0 = cmul(x0, hsx[hh].rot_neg[s]);
                     a0 = cadd(a0, x0);
                     if (two) {
                       float2 x1 = cmul_conj(y, __ldg(pp + s * L + 1));
-                      if (derot) x1 = cmul(x1, m.rot_neg[s]);
+                      if (derot) x1 = cmul(x1, hsx[hh].rot_neg[s]);
                       a1 = cadd(a1, x1);
                     }
                   }
@@ -506,61 +518,77 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 
         if (filt) {
           if (nv > 0) {
-            // one thread per (layer, edge, pilot): modulus / phase first, then every thread fits the two
+            // one thread per (hop, layer, edge, pilot): modulus / phase first, then every thread fits the two
             // lines of its edge and evaluates its own virtual pilot
-            const int l = tid / (2 * nv), r = tid - l * 2 * nv, end = r / nv, k = r - end * nv;
-            float2* const x = ext + l * EF + pad;              // x[0..nv) virtual | x[nv..nv+N) real | virtual
-            if (tid < 2 * LB * nv) {
+            const int per_hop = 2 * LB * nv;
+            const int hh = tid / per_hop, t = tid - hh * per_hop;
+            const int l = t / (2 * nv), r = t - l * 2 * nv, end = r / nv, k = r - end * nv;
+            const bool mine_vp = tid < n_hops * per_hop;
+            float2* const x = ext + (mine_vp ? hh : 0) * P.ext_hop + l * EF + pad;   // x[0..nv) virtual | x[nv..nv+N) real | virtual
+            HopScratch& hs = hsx[mine_vp ? hh : 0];
+            if (mine_vp) {
               const float2 e = end ? x[nv + N - 1 - k] : x[nv + k];
-              m.vp_mod[l][end][k] = sqrtf(e.x * e.x + e.y * e.y);
-              m.vp_ph[l][end][k] = atan2f(e.y, e.x);
+              hs.vp_mod[l][end][k] = sqrtf(e.x * e.x + e.y * e.y);
+              hs.vp_ph[l][end][k] = atan2f(e.y, e.x);
             }
             sync_a<NA>();
-            if (tid < 2 * LB * nv) {
-              const float2 val = virtual_pilot(nv, P.vp_mx, P.vp_den, m.vp_mod[l][end], m.vp_ph[l][end], k);
+            if (mine_vp) {
+              const float2 val = virtual_pilot(nv, P.vp_mx, P.vp_den, hs.vp_mod[l][end], hs.vp_ph[l][end], k);
               if (end) x[nv + N + (nv - 1 - k)] = val;
               else x[k] = val;
             }
           }
           sync_a<NA>();
-          if (hh == 0 && bt == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
+          if (bt == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
           // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493);
           // two adjacent outputs per thread share all but one of their input samples
-          for (int l = 0; l < LB; ++l) {
-            const float2* const xl = ext + l * EF + nv + 2 * pad;    // tap k of output i multiplies xl[i - k]
-            float2* const hl = hbuf + (l_lo + l) * N;
-            for (int i = 2 * tid; i < N; i += 2 * kThreads) {
-              double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
-              const float2 t1 = (i + 1 < N) ? xl[i + 1] : make_float2(0.f, 0.f);
-              double tx1 = double(t1.x), ty1 = double(t1.y);
-              for (int k = 0; k < K; ++k) {
-                const float2 t0 = xl[i - k];
-                const double tx0 = double(t0.x), ty0 = double(t0.y), w = m.taps[k];
-                ar0 += w * tx0;
-                ai0 += w * ty0;
-                ar1 += w * tx1;
-                ai1 += w * ty1;
-                tx1 = tx0;
-                ty1 = ty0;
+#pragma unroll
+          for (int hh = 0; hh < n_hops; ++hh) {
+            for (int l = 0; l < LB; ++l) {
+              const float2* const xl = ext + hh * P.ext_hop + l * EF + nv + 2 * pad;    // tap k of output i multiplies xl[i - k]
+              float2* const hl = hall + hh * L * N + (l_lo + l) * N;
+              for (int i = 2 * tid; i < N; i += 2 * kThreads) {
+                double ar0 = 0.0, ai0 = 0.0, ar1 = 0.0, ai1 = 0.0;
+                const float2 t1 = (i + 1 < N) ? xl[i + 1] : make_float2(0.f, 0.f);
+                double tx1 = double(t1.x), ty1 = double(t1.y);
+                for (int k = 0; k < K; ++k) {
+                  const float2 t0 = xl[i - k];
+                  const double tx0 = double(t0.x), ty0 = double(t0.y), w = m.taps[k];
+                  ar0 += w * tx0;
+                  ai0 += w * ty0;
+                  ar1 += w * tx1;
+                  ai1 += w * ty1;
+                  tx1 = tx0;
+                  ty1 = ty0;
+                }
+                hl[i] = make_float2(float(ar0), float(ai0));
+                if (i + 1 < N) hl[i + 1] = make_float2(float(ar1), float(ai1));
               }
-              hl[i] = make_float2(float(ar0), float(ai0));
-              if (i + 1 < N) hl[i + 1] = make_float2(float(ar1), float(ai1));
             }
           }
           sync_a<NA>();
           if (P.blend && N > 2) {                      // ce_dl_cnn.py:712-717
-            float2* const hb0 = hbuf + l_lo * N;
-            for (int idx = tid; idx < N * LB; idx += kThreads) {
-              const int l = idx / N, i = idx - l * N;
-              const int il = (i == 0) ? 1 : i - 1, ir = (i == N - 1) ? N - 2 : i + 1;
-              const float2 a = hb0[l * N + il], b = hb0[idx], c = hb0[l * N + ir];
-              ext[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
-                                     float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
+#pragma unroll
+            for (int hh = 0; hh < n_hops; ++hh) {
+              float2* const hb0 = hall + hh * L * N + l_lo * N;
+              float2* const sc0 = ext + hh * P.ext_hop;
+              for (int idx = tid; idx < N * LB; idx += kThreads) {
+                const int l = idx / N, i = idx - l * N;
+                const int il = (i == 0) ? 1 : i - 1, ir = (i == N - 1) ? N - 2 : i + 1;
+                const float2 a = hb0[l * N + il], b = hb0[idx], c = hb0[l * N + ir];
+                sc0[idx] = make_float2(float(0.25 * double(a.x) + 0.5 * double(b.x) + 0.25 * double(c.x)),
+                                       float(0.25 * double(a.y) + 0.5 * double(b.y) + 0.25 * double(c.y)));
+              }
             }
             sync_a<NA>();
-            for (int idx = tid; idx < N * LB; idx += kThreads) {
-              const float2 s0 = hb0[idx], lp = ext[idx];
-              hb0[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
+#pragma unroll
+            for (int hh = 0; hh < n_hops; ++hh) {
+              float2* const hb0 = hall + hh * L * N + l_lo * N;
+              const float2* const sc0 = ext + hh * P.ext_hop;
+              for (int idx = tid; idx < N * LB; idx += kThreads) {
+                const float2 s0 = hb0[idx], lp = sc0[idx];
+                hb0[idx] = make_float2(s0.x + P.cnn_alpha * (lp.x - s0.x), s0.y + P.cnn_alpha * (lp.y - s0.y));
+              }
             }
             sync_a<NA>();
           }
@@ -568,88 +596,106 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       }  // group batches
 
       if (P.smoothing == SRSCE_SMOOTH_MEAN) {
-        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int l = 0; l < SRSCE_MAX_LAYERS; ++l) {
-          if (l < L) {
-            float sx = 0.f, sy = 0.f;
-            for (int i = tid; i < N; i += kThreads) {
-              const float2 t = hbuf[l * N + i];
-              sx += t.x;
-              sy += t.y;
+        for (int hh = 0; hh < n_hops; ++hh) {
+          float2* const hbuf = hall + hh * L * N;
+          double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int l = 0; l < SRSCE_MAX_LAYERS; ++l) {
+            if (l < L) {
+              float sx = 0.f, sy = 0.f;
+              for (int i = tid; i < N; i += kThreads) {
+                const float2 t = hbuf[l * N + i];
+                sx += t.x;
+                sy += t.y;
+              }
+              v[2 * l] = sx;
+              v[2 * l + 1] = sy;
             }
-            v[2 * l] = sx;
-            v[2 * l + 1] = sy;
           }
+          block_sum<NA, 8>(m, v);
+          const float inv_n = 1.0f / float(N);
+          for (int idx = tid; idx < N * L; idx += kThreads) {
+            const int l = idx / N;
+            hbuf[idx] = make_float2(float(m.tot[2 * l]) * inv_n, float(m.tot[2 * l + 1]) * inv_n);
+          }
+          sync_a<NA>();
         }
-        block_sum<NA, 8>(m, v);
-        const float inv_n = 1.0f / float(N);
-        for (int idx = tid; idx < N * L; idx += kThreads) {
-          const int l = idx / N;
-          hbuf[idx] = make_float2(float(m.tot[2 * l]) * inv_n, float(m.tot[2 * l + 1]) * inv_n);
-        }
-        sync_a<NA>();
       }
 
       // ---- the smoothed pilots of every hop are final: build the store-slot table (final CFO
-      //      rotation :922-929, allocation flags) and release the writer warps; the time alignment
-      //      and noise estimates below only read hall, concurrently with them
-      if (hh == n_hops - 1) {
-        build_store_table(m.col[hb_idx]);
-        write_symbol_rotation(u);
-        bar_arrive(kBarFull + hb_idx, kCtaThreads);
-      }
+      //      rotation :922-929, allocation flags) and release the writer warps; the noise estimate and
+      //      the time alignment below only read hall, concurrently with them
+      build_store_table(m.col[hb_idx]);
+      write_symbol_rotation(u);
+      bar_arrive(kBarFull + hb_idx, kCtaThreads);
 
       // ---- reconstruction, noise, RSRP (:701-730)
       {
-        float noise_part = 0.f, rsrp_part = 0.f;
+        double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};                    // per hop: epre, noise, rsrp
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g < G) {
-            const bool two = 2 * g + 1 < L;
-            for (int i = tid; i < N; i += kThreads) {
-              const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
-              const float2* yp = yh + (g * N + i) * S;
-              const float2 h0 = hbuf[2 * g * N + i];
-              const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
-              for (int s = 0; s < S; ++s) {
-                const float2 y = yp[s];
-                float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, m.rot_pos[s]) : h0);
-                if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, m.rot_pos[s]) : h1));
-                const float2 d = csub(y, cscale(e, beta));
-                noise_part += d.x * d.x + d.y * d.y;
+        for (int hh = 0; hh < n_hops; ++hh) {
+          const HopDev& H = P.hop[hh];
+          const int S = H.n_dmrs, col0 = H.pilot_col0;
+          const bool derot = S >= 2 && P.cfo_compensate;
+          const float2* const yh = ys + G * N * col0;
+          const float2* const hbuf = hall + hh * L * N;
+          float noise_part = 0.f, rsrp_part = 0.f;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (g < G) {
+              const bool two = 2 * g + 1 < L;
+              for (int i = tid; i < N; i += kThreads) {
+                const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
+                const float2* yp = yh + (g * N + i) * S;
+                const float2 h0 = hbuf[2 * g * N + i];
+                const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
+                for (int s = 0; s < S; ++s) {
+                  const float2 y = yp[s];
+                  float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, hsx[hh].rot_pos[s]) : h0);
+                  if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, hsx[hh].rot_pos[s]) : h1));
+                  const float2 d = csub(y, cscale(e, beta));
+                  noise_part += d.x * d.x + d.y * d.y;
+                }
               }
             }
           }
+          for (int idx = tid; idx < N * L; idx += kThreads) {
+            const float2 t = hbuf[idx];
+            rsrp_part += t.x * t.x + t.y * t.y;
+          }
+          v[3 * hh] = double(epre_part[hh]);
+          v[3 * hh + 1] = double(noise_part);
+          v[3 * hh + 2] = double(rsrp_part);
         }
-        for (int idx = tid; idx < N * L; idx += kThreads) {
-          const float2 t = hbuf[idx];
-          rsrp_part += t.x * t.x + t.y * t.y;
-        }
-        double v[3] = {double(epre_part), double(noise_part), double(rsrp_part)};
-        block_sum<NA, 3>(m, v);
+        block_sum<NA, 8>(m, v);
         if (tid == 0) {
-          m.acc[0] += double(float(m.tot[0]));
-          m.acc[1] += double(float(m.tot[1]));
-          m.acc[2] += beta_d * beta_d * double(float(m.tot[2])) * double(S);
+          // float32 totals per hop and per quantity, accumulated in float64 like the reference's scalar accumulators
+#pragma unroll
+          for (int hh = 0; hh < n_hops; ++hh) {
+            m.acc[0] += double(float(m.tot[3 * hh]));
+            m.acc[1] += double(float(m.tot[3 * hh + 1]));
+            m.acc[2] += beta_d * beta_d * double(float(m.tot[3 * hh + 2])) * double(P.hop[hh].n_dmrs);
+          }
         }
       }
       sync_a<NA>();
-      if (P.y_bufs == 1 && hh == n_hops - 1) {                  // single staging buffer: this unit's pilot REs are dead now;
+      if (P.y_bufs == 1) {                                      // single staging buffer: this unit's pilot REs are dead now;
         stage_unit(u + gridDim.x, ystage);                     // the next unit's arrive while the IFFT below runs
         cp_async_commit();
       }
 
-      // ---- time alignment (:674-698)
+      // ---- time alignment (:674-698): IFFT of every (hop, layer) vector, fft_layers at a time
       {
         const int M = P.fft_size, log2M = 31 - __clz(M);
         const int* posl = m.re_pos[G - 1];
-        for (int lb = 0; lb < L; lb += P.fft_layers) {
-          const int nl = min(P.fft_layers, L - lb);
+        const int n_vec = n_hops * L;
+        for (int vb = 0; vb < n_vec; vb += P.fft_layers) {
+          const int nl = min(P.fft_layers, n_vec - vb);
           if (P.fft_regular) {
             for (int idx = tid; idx < nl * M; idx += kThreads) {
-              const int l = idx >> log2M, n = idx & (M - 1);
-              ext[idx] = (n < N) ? hbuf[(lb + l) * N + n] : make_float2(0.f, 0.f);
+              const int v = vb + (idx >> log2M), n = idx & (M - 1);     // vector v = hop * L + layer: hall is [hop][layer][N]
+              ext[idx] = (n < N) ? hall[v * N + n] : make_float2(0.f, 0.f);
             }
           } else {
             for (int idx = tid; idx < nl * M; idx += kThreads) ext[idx] = make_float2(0.f, 0.f);
@@ -657,7 +703,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             for (int idx = tid; idx < nl * N; idx += kThreads) {
               const int l = idx / N, i = idx - l * N;
               const int q = i / R;
-              ext[l * M + q * kNRE + posl[i - q * R] - posl[0]] = hbuf[(lb + l) * N + i];
+              ext[l * M + q * kNRE + posl[i - q * R] - posl[0]] = hall[(vb + l) * N + i];
             }
           }
           sync_a<NA>();
@@ -665,21 +711,22 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           for (int t = tid; t < 2 * SRSCE_TA_WINDOW; t += kThreads) {
             const int bin = (t < SRSCE_TA_WINDOW) ? t : SRSCE_TA_FFT - 2 * SRSCE_TA_WINDOW + t;
             const int pos = dif_position(bin & (M - 1), M);
-            float acc = (lb == 0) ? 0.f : m.prof[t];
-            for (int l = 0; l < nl; ++l) {
+            for (int l = 0; l < nl; ++l) {                       // layers are summed in order within their hop's profile
+              const int v = vb + l, hh = (TWO_HOPS && v >= L) ? 1 : 0;
               const float2 z = ext[l * M + pos];
-              acc += z.x * z.x + z.y * z.y;
+              const float pw = z.x * z.x + z.y * z.y;
+              hsx[hh].prof[t] = (v == hh * L) ? pw : hsx[hh].prof[t] + pw;
             }
-            m.prof[t] = acc;
           }
           sync_a<NA>();
         }
-        if (warp == 0) {
+        if (warp < n_hops) {
           // first maximum of each window; ties keep the lower index, as torch.max / np.argmax
+          const float* prof = hsx[warp].prof;
           float bd = -1.f, ba = -1.f;
           int id = 0, ia = 0;
           for (int t = lane; t < SRSCE_TA_WINDOW; t += 32) {
-            const float d = m.prof[t], a = m.prof[SRSCE_TA_WINDOW + t];
+            const float d = prof[t], a = prof[SRSCE_TA_WINDOW + t];
             if (d > bd) { bd = d; id = t; }
             if (a > ba) { ba = a; ia = t; }
           }
@@ -692,12 +739,16 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
           if (lane == 0) {
             const int imax = (bd >= ba) ? id : -(SRSCE_TA_WINDOW - ia);
-            m.acc[3] += double(imax) / double(SRSCE_TA_FFT) / P.scs_hz;
+            m.ta_hop[warp] = double(imax) / double(SRSCE_TA_FFT) / P.scs_hz;
           }
         }
       }
-      sync_a<NA>();   // ext (IFFT scratch) and the profile are rewritten by the next hop / unit
-    }  // hops
+      sync_a<NA>();   // ext (IFFT scratch), the profiles and ta_hop are complete
+      if (tid == 0) {
+#pragma unroll
+        for (int hh = 0; hh < n_hops; ++hh) m.acc[3] += m.ta_hop[hh];
+      }
+    }
 
     if (dbg & 1) {                                            // profiling ablation: writers run on stale pilots
       if (wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);

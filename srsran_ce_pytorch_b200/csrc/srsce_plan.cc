@@ -462,9 +462,9 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       const int ext_layers = slim ? std::min(L, 2) : L;
       v.fir_per_group = (slim && L > 2) ? 1 : 0;
       v.fft_layers = slim ? std::min(fft_default, 2) : fft_default;
-      int ext = fir_len * ext_layers;                                // FIR input incl. virtual pilots and zero margins
+      v.ext_hop = fir_len * ext_layers;                              // FIR input incl. virtual pilots and zero margins, per hop
+      int ext = n_hops * v.ext_hop;                                 // (also the scratch of the CNN blend: N * layers <= ext_hop)
       ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
-      ext = std::max(ext, N * ext_layers);                          // scratch of the CNN blend
       const int tile_elems = writer_warps(na) * kTileRows * L * n_hops;
       v.ext_elems = ext;
       v.est_threads = na;
@@ -475,7 +475,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       v.off_ext = v.off_y + up16(y_bufs * y_unit * 8);
       v.off_tile = v.off_ext + up16(ext * 8);
       v.off_misc = v.off_tile + up16(tile_elems * 8);
-      v.smem_bytes = v.off_misc + kMiscBytes;
+      v.smem_bytes = v.off_misc + kMiscBytes + n_hops * kHopScratchBytes;
       return v.smem_bytes;
     };
     const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
