@@ -50,6 +50,19 @@ __global__ void fill_units_linear(float4* out, int n_units, int n4_per_unit) {
   }
 }
 
+// block-cyclic chunks over the whole buffer: chunk c is written by CTA c % gridDim, each warp taking 512-B pieces;
+// the write fronts of all CTAs form one contiguous moving window (what a global tile queue would produce)
+template <int MODE>
+__global__ void fill_chunked(float4* out, size_t n4, int chunk4) {
+  const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+  const size_t n_chunks = n4 / chunk4;
+  for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    float4* base = out + c * (size_t)chunk4;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < chunk4; i += blockDim.x) store16<MODE>(base + i, v);
+  }
+}
+
 // TMA bulk store: stage 16 KB in shared memory once, then stream it out with cp.async.bulk
 __global__ void fill_bulk(char* out, int n_units, int bytes_per_unit, int chunk) {
   extern __shared__ __align__(128) char sm[];
@@ -113,6 +126,12 @@ int main() {
 #define RUN_UL(MODE, G, B) ms = time_ms([&] { fill_units_linear<MODE><<<G, B>>>(out, n_units, rows * cols); }); \
   printf("unitslin %-20s g=%5d b=%4d %8.3f ms %8.1f GB/s\n", names[MODE], G, B, ms, gb / ms * 1e3);
   RUN_UL(0, sms * 3, 256) RUN_UL(1, sms * 3, 256) RUN_UL(1, sms * 8, 256) RUN_UL(1, sms * 2, 1024)
+  for (int chunk4 : {896, 3584, 28 * 3276 / 4}) {            // 14 KB tile, 57 KB, a quarter unit
+    for (int g : {sms * 2, sms * 3, sms * 8}) {
+      ms = time_ms([&] { fill_chunked<1><<<g, 192>>>(out, n4, chunk4); });
+      printf("chunked  st.cs chunk=%7d B g=%5d b= 192 %8.3f ms %8.1f GB/s\n", chunk4 * 16, g, ms, gb / ms * 1e3);
+    }
+  }
   for (int chunk : {4096, 16384, 65536}) {
     CK(cudaFuncSetAttribute(fill_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk));
     for (int per : {1, 2, 4}) {
