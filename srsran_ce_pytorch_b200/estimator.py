@@ -209,6 +209,11 @@ def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fi
             raise AssertionError("Hops should not overlap.")                                    # :862
         assert rm1.shape == rm2.shape and np.array_equal(rm1, rm2), \
             "The DM-RS mask should be the same for the two hops."                               # :869
+    if desc.cfo_compensate and n_sym != 14 and desc.n_cp >= 14 and any(
+            bin(h.dmrs_symbol_mask).count("1") >= 2 for h in (h1, h2)):
+        # the reference indexes its 14-entry phase table with the grid's symbol mask (:717) and broadcasts it over
+        # the grid (:929): both fail with an IndexError-class shape mismatch unless the grid has 14 symbols
+        raise IndexError(f"CFO compensation with two pilot symbols in a hop needs a 14-symbol grid (got {n_sym})")
     n_cdm = (n_layers + 1) // 2
     if rm1.shape[1] < n_cdm:
         raise IndexError(f"DMRSREmask has {rm1.shape[1]} columns, {n_cdm} CDM groups needed")

@@ -99,6 +99,9 @@ def test_error_behaviour_matches_reference():
         estimator.make_plan(52, 14, 1, hop1, hop2, cfg)
     with pytest.raises(NotImplementedError):                             # n_sc > 4096: the TA IFFT would truncate
         estimator.make_plan(400, 14, 1, synth.make_hop(400, 0, 4, [2], "comb2", 1), synth.no_hop(), cfg)
+    short = synth.make_hop(52, 3, 4, [0, 1], "comb2", 1, n_sym=2)
+    with pytest.raises(IndexError):                                      # (n_sc, 2) grid + CFO on
+        estimator.make_plan(52, 2, 1, short, synth.no_hop(), cfg)
     bad = synth.make_hop(52, 3, 4, [2, 11], "comb2", 1)
     bad.maskPRBs[30] = True
     with pytest.raises(ValueError, match="contiguous"):
