@@ -1,5 +1,6 @@
 """Randomised differential test: arbitrary 12-bit RE masks (irregular combs, R not dividing 12), odd pilot
 counts, 1-PRB hops, every smoothing / CFO / fill combination -- CUDA path vs the oracle."""
+import os
 import random
 
 import numpy as np
@@ -42,7 +43,8 @@ def _cases(n=48, seed=777):
     return out
 
 
-CASES = _cases()
+# FUZZ_N / FUZZ_SEED widen the campaign for one-off hunts (the default set is what CI runs)
+CASES = _cases(int(os.environ.get("FUZZ_N", "48")), int(os.environ.get("FUZZ_SEED", "777")))
 
 
 @pytest.mark.parametrize("k", range(len(CASES)))
