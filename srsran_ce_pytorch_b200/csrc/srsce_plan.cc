@@ -448,10 +448,13 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   //      11 % of the headline throughput.
   //   B  the same CTA shape with a slimmer footprint: one staging buffer (the next unit's pilot REs are fetched
   //      while the IFFT runs), FIR input one CDM group at a time, IFFT two layers at a time.
-  //   C  one CTA of 512 estimator threads (+8 writer warps) with the slim footprint.
-  //   Measured on B200 (comb-2, 273 PRB): the smaller the footprint, the faster -- phase A re-reads the pilots
-  //   through L1, and L1 is what shared memory leaves over: 127 KB 0.59, 153 KB 0.57, 174 KB 0.58, 180 KB 0.54,
-  //   206 KB (smoothed pilots double buffered) 0.50 of the HBM peak.
+  //   C  one CTA of 512 estimator threads (+8 writer warps), one staging buffer, FIR input for all layers (the
+  //      stretch between "writers done" and "next FIR done" is shortest when both CDM groups are de-spread ahead).
+  //   D  the same with the slim footprint (the largest geometries).
+  //   Measured on B200 (comb-2, 273 PRB): single staging buffer 0.60 (C) / 0.59 (D), two staging buffers 0.58 / 0.57,
+  //   smoothed pilots double buffered 0.50-0.54 of the HBM peak -- phase A re-reads the pilots through L1, the
+  //   gather of the next unit pollutes L1 unless it is issued after the noise estimate, and L1 is what shared
+  //   memory leaves over.
   {
     const int h_elems = n_hops * N * L;
     const int y_unit = G * N * s_total;
@@ -480,7 +483,9 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     };
     const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
     (void)one_cta_l1_budget;
-    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget) layout(512, 1, 1, true);
+    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
+        layout(512, 1, 1, false) > 227 * 1024)
+      layout(512, 1, 1, true);
     if (const char* e = getenv("SRSCE_DEBUG_LAYOUT")) {       // experiments only: "na,hall_bufs,y_bufs,slim"
       int na = 256, hb = 1, yb = 2, sl = 0;
       if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512)) layout(na, hb, yb, sl != 0);
