@@ -305,6 +305,27 @@ def run_ours(args):
                "kernel_ms": alt_ms, "n_gpus": 1}
         del rx_sm
 
+    # ---- one received grid per (slot, rx antenna), shared by the UEs multiplexed on it (what a caller of the reference
+    #      does by passing the same tensor to 64 calls): srsce_estimate_indexed, no copies materialised
+    shared = None
+    if not args.no_alt_layout:
+        grids = rx.view(args.slots, UES, RX_ANT, 12 * N_PRB, N_SYM)[:, 0].reshape(args.slots * RX_ANT, 12 * N_PRB, N_SYM).contiguous()
+        unit = torch.arange(n_local, device=dev)
+        rx_index = ((unit // UNITS_PER_SLOT) * RX_ANT + unit % RX_ANT).to(torch.int64)
+        for _ in range(3):
+            plan.estimate_indexed(grids, rx_index, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(args.steps):
+            plan.estimate_indexed(grids, rx_index, pil, 1.0, RX_ANT, out=out, scalars=sc)
+        s1.record()
+        torch.cuda.synchronize()
+        sms_ = s0.elapsed_time(s1) / args.steps
+        shared = {"rx": "one grid per (slot, rx antenna) shared by the slot's UEs (srsce_estimate_indexed)",
+                  "value": LAYERS * n_local / (sms_ * 1e-3), "unit": UNIT, "kernel_ms": sms_, "n_gpus": 1}
+        del grids
+
     # ---- compact output (srsce_estimate_compact, SURVEY 8f-2: outside the reference contract, reported separately)
     compact = None
     if not args.no_alt_layout:
@@ -387,6 +408,10 @@ def run_ours(args):
                     "steps": e2e_steps, "units_per_step": n_e2e, "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": sampler.summary(wall0, wall1),
         }
+        if shared is not None:
+            shared["roofline_frac"] = (bpu - 8 * 2 * N_PRB * 3 * len(PILOT_SYMBOLS) * (UES - 1) // UES) * n_local / \
+                (shared["kernel_ms"] * 1e-3) / 1e9 / peak
+            line["shared_rx_grids"] = shared
         if compact is not None:
             line["compact_output"] = compact
         if alt is not None:

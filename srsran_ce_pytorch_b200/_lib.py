@@ -63,6 +63,9 @@ def _load() -> C.CDLL:
     lib.srsce_estimate_compact.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_int32,
                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.srsce_estimate_compact.restype = C.c_int
+    lib.srsce_estimate_indexed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.srsce_estimate_indexed.restype = C.c_int
     lib.srsce_last_launch_count.restype = C.c_int
     if lib.srsce_abi_version() != ABI_VERSION:
         raise ImportError(f"libsrsce.so ABI {lib.srsce_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
@@ -72,7 +75,8 @@ def _load() -> C.CDLL:
 lib = _load()
 
 EXPORTS = ("srsce_abi_version", "srsce_last_error", "srsce_plan_create", "srsce_plan_destroy", "srsce_plan_query",
-           "srsce_plan_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_last_launch_count")
+           "srsce_plan_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed",
+           "srsce_last_launch_count")
 
 
 def last_error() -> str:

@@ -131,6 +131,30 @@ int srsce_estimate_compact(const srsce_plan* plan, const void* rx_grid, const in
   }
 }
 
+int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const int64_t rx_strides[3],
+                           const int64_t* rx_index, const void* pilots, int32_t pilot_share, double beta, void* ch_est,
+                           double* scalars, int64_t n_units, void* stream) {
+  g_launches = 0;
+  if (!plan || !rx_strides) return fail(SRSCE_ERR_INVALID, "null argument");
+  if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
+  if (n_units > 0 && (!rx_grids || !rx_index || !pilots || !ch_est || !scalars)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if (pilot_share < 1 || (n_units % pilot_share) != 0)
+    return fail(SRSCE_ERR_INVALID, "n_units must be a multiple of pilot_share (>= 1)");
+  if (!(beta != 0.0)) return fail(SRSCE_ERR_INVALID, "beta_dmrs must be non-zero");
+  if ((reinterpret_cast<uintptr_t>(ch_est) & 15u) || (reinterpret_cast<uintptr_t>(rx_grids) & 7u) ||
+      (reinterpret_cast<uintptr_t>(pilots) & 7u) || (reinterpret_cast<uintptr_t>(scalars) & 7u) ||
+      (reinterpret_cast<uintptr_t>(rx_index) & 7u))
+    return fail(SRSCE_ERR_INVALID, "buffers must be aligned (ch_est 16 B, others 8 B)");
+  try {
+    std::string err;
+    const int rc = srsce::launch_estimate(plan->impl, rx_grids, rx_strides, pilots, pilot_share, beta, ch_est, scalars,
+                                          n_units, stream, &g_launches, err, nullptr, nullptr, rx_index);
+    return rc == SRSCE_OK ? rc : fail(rc, err);
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
 int srsce_last_launch_count(void) { return g_launches; }
 
 }  // extern "C"

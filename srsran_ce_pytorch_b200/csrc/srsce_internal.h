@@ -121,7 +121,7 @@ void release_plan(Plan& p);
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots,
                     int pilot_share, double beta, void* out, double* scalars, int64_t n_units,
                     void* stream, int* launches, std::string& err, void* out_compact = nullptr,
-                    void* rot_compact = nullptr);
+                    void* rot_compact = nullptr, const int64_t* rx_index = nullptr);
 int max_dynamic_smem();
 
 }  // namespace srsce

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 6 : 8), NA == 256 ? 2 :
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg,
-                float2* __restrict__ out_c, float2* __restrict__ rot_c) {
+                float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index) {
   constexpr int kThreads = NA;                              // estimator threads
   constexpr int kWarpsB = (NA == 256) ? 6 : 8;            // = writer_warps(NA)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
@@ -332,7 +332,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
     if (un >= n_units || (dbg & 4)) return;                    // (ablation bit 2: no staging traffic)
-    const float2* rxn = rx + un * su;
+    const float2* rxn = rx + (rx_index ? __ldg(rx_index + un) : un) * su;     // several units may share one received grid
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
       float2* const d0 = dst + G * N * H.pilot_col0;
@@ -953,7 +953,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 }
 
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
-                         double, float2*, double*, long long, int, float2*, float2*);
+                         double, float2*, double*, long long, int, float2*, float2*, const long long*);
 
 template <int NA>
 KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
@@ -1058,7 +1058,7 @@ void release_plan(Plan& p) {
 
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots, int pilot_share,
                     double beta, void* out, double* scalars, int64_t n_units, void* stream, int* launches,
-                    std::string& err, void* out_compact, void* rot_compact) {
+                    std::string& err, void* out_compact, void* rot_compact, const int64_t* rx_index) {
   *launches = 0;
   if (p.device < 0) { err = "plan has no CUDA device (created without a GPU); there is no CPU compute path"; return SRSCE_ERR_NO_DEVICE; }
   int dev = -1;
@@ -1071,7 +1071,8 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   fn<<<grid, cta_threads(p.dev.est_threads), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
-      debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact));
+      debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact),
+      reinterpret_cast<const long long*>(rx_index));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = cuda_msg("kernel launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;

@@ -142,6 +142,41 @@ class Plan:
             raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
         return n_units, (pilots if pilots.is_contiguous() else pilots.contiguous())
 
+    def estimate_indexed(self, rx_grids: torch.Tensor, rx_index: torch.Tensor, pilots: torch.Tensor, beta: float,
+                         pilot_share: int = 1, out: Optional[torch.Tensor] = None,
+                         scalars: Optional[torch.Tensor] = None):
+        """Like ``estimate`` but unit u reads received grid ``rx_grids[rx_index[u]]``: the way to hand the same
+        grid (one rx antenna, one slot) to the units of every UE multiplexed on it, as a caller of the reference
+        does by passing the same tensor to several calls.  rx_grids [n_grids, n_sc, n_sym]; rx_index int64 [B]."""
+        i = self.info
+        if not rx_grids.is_cuda or not pilots.is_cuda or not rx_index.is_cuda:
+            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
+        if rx_grids.dtype != torch.complex64 or pilots.dtype != torch.complex64 or rx_index.dtype != torch.int64:
+            raise TypeError("rx_grids / pilots must be complex64 and rx_index int64")
+        if rx_grids.dim() != 3 or tuple(rx_grids.shape[1:]) != (i.n_sc, i.n_sym):
+            raise IndexError(f"received grids shape {tuple(rx_grids.shape)} != [G, {i.n_sc}, {i.n_sym}]")
+        n_units = int(rx_index.numel())
+        if pilot_share < 1 or n_units % pilot_share:
+            raise ValueError("number of units must be a multiple of pilot_share")
+        want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
+        if tuple(pilots.shape) != want:
+            raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
+        if n_units and (int(rx_index.min()) < 0 or int(rx_index.max()) >= rx_grids.shape[0]):
+            raise IndexError("rx_index out of range")
+        pilots = pilots if pilots.is_contiguous() else pilots.contiguous()
+        rx_index = rx_index.contiguous()
+        if out is None:
+            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=rx_grids.device)
+        if scalars is None:
+            scalars = torch.empty((n_units, 6), dtype=torch.float64, device=rx_grids.device)
+        strides = (C.c_int64 * 3)(*rx_grids.stride())
+        with torch.cuda.device(rx_grids.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.raise_for(lib.srsce_estimate_indexed(self._h, rx_grids.data_ptr(), strides, rx_index.data_ptr(),
+                                                      pilots.data_ptr(), int(pilot_share), float(beta), out.data_ptr(),
+                                                      scalars.data_ptr(), n_units, C.c_void_p(stream)))
+        return out, scalars
+
     def estimate_compact(self, rx: torch.Tensor, pilots: torch.Tensor, beta: float, pilot_share: int = 1):
         """Compact output (not part of the reference contract): returns (ch_sc [B, n_hops, n_sc, L],
         sym_rot [B, n_sym], scalars [B, 6]); ``expand_compact`` rebuilds the dense grid."""

@@ -280,3 +280,17 @@ def test_persistent_loop_full_band_layouts(pattern, syms, n_units):
         s = sc[(reps - 1) * gen + b].cpu().numpy()
         tol.check_scalars([s[0], s[1], s[2], s[3], s[4] if s[5] else None], want[1:], 30e3, diag["ta_margin"],
                           tag=f"layouts/{pattern}/{b}")
+
+
+def test_indexed_received_grids_equal_materialised_copies():
+    """srsce_estimate_indexed: unit u reads rx_grids[rx_index[u]] -- bit-identical to gathering the grids first."""
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(32)
+    plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    grids = data["rx"][:4].contiguous()                          # 4 rx antennas of one slot ...
+    idx = (torch.arange(32, device="cuda") % 4).to(torch.int64)  # ... shared by the 8 UEs (unit = ue * 4 + antenna)
+    a, sa = plan.estimate_indexed(grids, idx, data["pilots"], 1.0, 4)
+    b, sb = plan.estimate(grids[idx].contiguous(), data["pilots"], 1.0, 4)
+    assert torch.equal(a, b) and torch.equal(sa, sb)
+    with pytest.raises(IndexError):
+        plan.estimate_indexed(grids, idx + 1, data["pilots"], 1.0, 4)
