@@ -331,7 +331,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   // ================================ estimator warps ==========================================
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
-    if (un >= n_units || (dbg & 4)) return;                    // (ablation bit 2: no staging traffic)
+    if (un >= n_units || (dbg & 4) || P.y_bufs == 0) return;   // (ablation bit 2 / unstaged fallback: no staging traffic)
     const float2* rxn = rx + (rx_index ? __ldg(rx_index + un) : un) * su;     // several units may share one received grid
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
@@ -382,6 +382,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
     const float2* const ys = ystage + ((P.y_bufs == 2) ? (it & 1) * ylen : 0);
+    // received pilot RE (hop H, group g, pilot i, pilot symbol s): from the staged copy, or -- the fallback for
+    // geometries whose staging buffer does not fit beside the rest -- straight from the received grid
+    const float2* const rxu = rx + (rx_index ? __ldg(rx_index + u) : u) * su;
+    auto ld_y = [&](const HopDev& H, int g, int i, int s) -> float2 {
+      if (P.y_bufs != 0) return ys[G * N * H.pilot_col0 + (g * N + i) * H.n_dmrs + s];
+      return __ldg(rxu + (long long)pilot_sc(m, H.band_sc0, R, g, i) * ssc + (long long)H.sym_idx[s] * ssym);
+    };
     const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
     float2* const hall = hall0 + hb_idx * (n_hops * L * N);
     const bool wait_empty = it >= P.hall_bufs;                 // the writers last used this buffer hall_bufs units ago
@@ -402,13 +409,12 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         const HopDev& H = P.hop[hh];
         const int S = H.n_dmrs, col0 = H.pilot_col0;
         if (S < 2) continue;
-        const float2* const yh = ys + G * N * col0;           // [group][pilot][symbol] of this hop
         float2 c[2][2] = {{{0.f, 0.f}, {0.f, 0.f}}, {{0.f, 0.f}, {0.f, 0.f}}};
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           if (g < G) {
             for (int i = tid; i < N; i += kThreads) {
-              const float2 y0 = yh[(g * N + i) * S], y1 = yh[(g * N + i) * S + 1];
+              const float2 y0 = ld_y(H, g, i, 0), y1 = ld_y(H, g, i, 1);
               const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -458,7 +464,6 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           const HopDev& H = P.hop[hh];
           const int S = H.n_dmrs, col0 = H.pilot_col0;
           const bool derot = S >= 2 && P.cfo_compensate;
-          const float2* const yh = ys + G * N * col0;
           float2* const exth = ext + hh * P.ext_hop;
           float2* const dst = filt ? exth + pad + nv : hall + hh * L * N;   // filt: layer index relative to the batch
           const int dstride = filt ? EF : N;
@@ -481,9 +486,8 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 float2 a0 = make_float2(0.f, 0.f), a1 = a0;
                 if (i < N) {
                   const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
-                  const float2* yp = yh + (g * N + i) * S;
                   for (int s = 0; s < S; ++s) {
-                    const float2 y = yp[s];
+                    const float2 y = ld_y(H, g, i, s);
                     epre_part[hh] += y.x * y.x + y.y * y.y;
                     float2 x0 = cmul_conj(y, __ldg(pp + s * L));
                     if (derot) x0 = cmul(x0, hsx[hh].rot_neg[s]);
@@ -638,7 +642,6 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           const HopDev& H = P.hop[hh];
           const int S = H.n_dmrs, col0 = H.pilot_col0;
           const bool derot = S >= 2 && P.cfo_compensate;
-          const float2* const yh = ys + G * N * col0;
           const float2* const hbuf = hall + hh * L * N;
           float noise_part = 0.f, rsrp_part = 0.f;
 #pragma unroll
@@ -647,11 +650,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               const bool two = 2 * g + 1 < L;
               for (int i = tid; i < N; i += kThreads) {
                 const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
-                const float2* yp = yh + (g * N + i) * S;
                 const float2 h0 = hbuf[2 * g * N + i];
                 const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
                 for (int s = 0; s < S; ++s) {
-                  const float2 y = yp[s];
+                  const float2 y = ld_y(H, g, i, s);
                   float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, hsx[hh].rot_pos[s]) : h0);
                   if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, hsx[hh].rot_pos[s]) : h1));
                   const float2 d = csub(y, cscale(e, beta));

@@ -451,6 +451,8 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   //   C  one CTA of 512 estimator threads (+8 writer warps), one staging buffer, FIR input for all layers (the
   //      stretch between "writers done" and "next FIR done" is shortest when both CDM groups are de-spread ahead).
   //   D  the same with the slim footprint (the largest geometries).
+  //   E  D without a staging buffer: the pilot REs are read from the received grid where they are used (dense
+  //      masks with several pilot symbols; everything with n_sc <= 4096 and <= 4 layers fits).
   //   Measured on B200 (comb-2, 273 PRB): single staging buffer 0.60 (C) / 0.59 (D), two staging buffers 0.58 / 0.57,
   //   smoothed pilots double buffered 0.50-0.54 of the HBM peak -- phase A re-reads the pilots through L1, the
   //   gather of the next unit pollutes L1 unless it is issued after the noise estimate, and L1 is what shared
@@ -484,8 +486,8 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
     (void)one_cta_l1_budget;
     if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
-        layout(512, 1, 1, false) > 227 * 1024)
-      layout(512, 1, 1, true);
+        layout(512, 1, 1, false) > 227 * 1024 && layout(512, 1, 1, true) > 227 * 1024)
+      layout(512, 1, 0, true);
     if (const char* e = getenv("SRSCE_DEBUG_LAYOUT")) {       // experiments only: "na,hall_bufs,y_bufs,slim"
       int na = 256, hb = 1, yb = 2, sl = 0;
       if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512)) layout(na, hb, yb, sl != 0);

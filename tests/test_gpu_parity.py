@@ -253,14 +253,17 @@ def test_short_and_odd_grids_match_oracle(case, two_hops):
         tol.check_scalars(got, want[1:], 30e3, diag["ta_margin"], tag=f"{case}/{two_hops}/{b}")
 
 
-@pytest.mark.parametrize("pattern,syms,n_units", [("comb4", [3, 10], 720), ("comb2", [13], 400), ("comb2", [3, 10], 330),
-                                                   ("type2", [6], 640), ("comb4", [2, 5, 8, 11], 340)],
-                         ids=["slim-2cta-S2", "one-cta-comb2", "one-cta-comb2-S2", "slim-type2", "one-cta-S4"])
-def test_persistent_loop_full_band_layouts(pattern, syms, n_units):
+@pytest.mark.parametrize("pattern,syms,n_units,grid", [("comb4", [3, 10], 720, 273), ("comb2", [13], 400, 273),
+                                                        ("comb2", [3, 10], 330, 273), ("type2", [6], 640, 273),
+                                                        ("comb4", [2, 5, 8, 11], 340, 273), ("dense", [3, 10], 320, 273),
+                                                        ("comb2", [1, 4, 8, 12], 320, 341)],
+                         ids=["slim-2cta-S2", "one-cta-comb2", "one-cta-comb2-S2", "slim-type2", "one-cta-S4",
+                              "unstaged-dense-S2", "unstaged-341prb-S4"])
+def test_persistent_loop_full_band_layouts(pattern, syms, n_units, grid):
     """Full-band geometries that select the other shared-memory layouts (single staging buffer, per-group FIR
     input, one 768-thread CTA per SM), with more units than resident CTAs so that every CTA pipelines several."""
     from srsran_ce_pytorch_b200 import estimator, synth
-    hop1 = synth.make_hop(273, 0, 273, syms, pattern, 2)
+    hop1 = synth.make_hop(grid, 0, grid, syms, pattern, 2)
     cfg = synth.make_config(30e3, "filter", True)
     gen = 20
     data = synth.make_units(hop1, synth.no_hop(), cfg, 4, gen, pilot_share=4, seed=21, device="cuda")
