@@ -69,7 +69,7 @@ int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info) {
   info->fft_size = v.fft_size;
   info->cfo_defined = v.cfo_defined;
   info->smem_bytes = v.smem_bytes;
-  info->threads = srsce::cta_threads(v.est_threads);
+  info->threads = srsce::cta_threads(v.est_threads, v.n_hops == 2);
   info->fill_terms = plan->impl.fill_terms_host;
   info->has_device = plan->impl.device >= 0;
   info->bytes_per_unit = plan->impl.bytes_per_unit;

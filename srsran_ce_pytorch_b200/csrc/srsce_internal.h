@@ -16,11 +16,16 @@ namespace srsce {
 constexpr int kNRE = 12;              // resource elements per PRB
 // A CTA = NA estimator threads (phase A: pilots -> smoothed channel + scalars) + writer warps (phase B:
 // interpolate + stream the dense grid out).  Geometries whose shared-memory footprint allows two CTAs
-// per SM run NA = 256 (+6 writer warps); heavier ones run one CTA of NA = 512 (+8 writer warps).
+// per SM run NA = 256 (+4 writer warps, 6 with two hops); heavier ones run one CTA of NA = 512 (+6 / 8 writer warps).
 constexpr int kMaxWarpsA = 16;
 constexpr int kMaxWarpsB = 8;
-constexpr int writer_warps(int na) { return na == 256 ? 6 : 8; }
-constexpr int cta_threads(int na) { return na + 32 * writer_warps(na); }
+// Writer warps per CTA, measured on B200 at BASELINE config 2 (fraction of the HBM peak, same box):
+//   two CTAs of 256 estimator threads: 4 warps 0.852 | 5 warps 0.832 | 6 warps 0.834
+//   one CTA of 512 estimator threads:  3 warps 0.80 | 4-5 warps 0.85 | 6 warps 0.880 | 8 warps 0.870 | 10 warps 0.84 | 12 warps 0.82
+// More writers than the store stream needs only add contention for phase A's loads.  Two-hop units do more work per
+// stored row (two sources, per-symbol select) and keep the larger teams: 6 / 8 warps measure 4-12 % faster there.
+constexpr int writer_warps(int na, bool two_hops) { return na == 256 ? (two_hops ? 6 : 4) : (two_hops ? 8 : 6); }
+constexpr int cta_threads(int na, bool two_hops) { return na + 32 * writer_warps(na, two_hops); }
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
 constexpr int kCnnEdgeRows = 2 * kNRE; // band rows at either end whose CNN operator rows are looked up individually

@@ -287,14 +287,14 @@ __device__ __forceinline__ void stream_full_tile_2hop(const float4* __restrict__
 //   ext[layer][EF]             raw pilots with nv virtual pilots and `pad` zeros either side (FIR input),
 //                              EF = N + 2*nv + 2*pad; later the FFT scratch
 //   tiles[writer warp][hop][32][L]  interpolated rows being streamed out
-template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT>
-__global__ void __launch_bounds__(NA + 32 * (NA == 256 ? 6 : 8), NA == 256 ? 2 : 1)
+template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT, bool STAGED>
+__global__ void __launch_bounds__(cta_threads(NA, TWO_HOPS), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg,
                 float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index) {
   constexpr int kThreads = NA;                              // estimator threads
-  constexpr int kWarpsB = (NA == 256) ? 6 : 8;            // = writer_warps(NA)
+  constexpr int kWarpsB = (NA == 256) ? (TWO_HOPS ? 6 : 4) : (TWO_HOPS ? 8 : 6);   // = writer_warps(NA, TWO_HOPS)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
   extern __shared__ __align__(16) unsigned char smem[];
   float2* const hall0 = reinterpret_cast<float2*>(smem + P.off_h);     // hall_bufs buffers of n_hops*L*N
@@ -331,7 +331,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   // ================================ estimator warps ==========================================
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
-    if (un >= n_units || (dbg & 4) || P.y_bufs == 0) return;   // (ablation bit 2 / unstaged fallback: no staging traffic)
+    if ((!STAGED && P.y_bufs == 0) || un >= n_units || (dbg & 4)) return;          // (unstaged fallback / ablation bit 2: no staging traffic)
     const float2* rxn = rx + (rx_index ? __ldg(rx_index + un) : un) * su;     // several units may share one received grid
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
@@ -383,10 +383,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     sync_a<NA>();                                                 // ... for every estimator thread
     const float2* const ys = ystage + ((P.y_bufs == 2) ? (it & 1) * ylen : 0);
     // received pilot RE (hop H, group g, pilot i, pilot symbol s): from the staged copy, or -- the fallback for
-    // geometries whose staging buffer does not fit beside the rest -- straight from the received grid
-    const float2* const rxu = rx + (rx_index ? __ldg(rx_index + u) : u) * su;
+    // geometries whose staging buffer does not fit beside the rest (STAGED = false, a separate instantiation so
+    // that the staged variants do not carry its address arithmetic) -- straight from the received grid
+    const float2* const rxu = STAGED ? rx : rx + (rx_index ? __ldg(rx_index + u) : u) * su;
     auto ld_y = [&](const HopDev& H, int g, int i, int s) -> float2 {
-      if (P.y_bufs != 0) return ys[G * N * H.pilot_col0 + (g * N + i) * H.n_dmrs + s];
+      // (the unstaged instantiation keeps the run-time test as well: with the shared-memory path compiled out, the
+      //  nvcc 12.9 build of this lambda faulted with an illegal address on B200 whenever a hop has two pilot symbols;
+      //  not understood -- DESIGN.md section 7)
+      if (STAGED || P.y_bufs != 0) return ys[G * N * H.pilot_col0 + (g * N + i) * H.n_dmrs + s];
       return __ldg(rxu + (long long)pilot_sc(m, H.band_sc0, R, g, i) * ssc + (long long)H.sym_idx[s] * ssym);
     };
     const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
@@ -957,19 +961,20 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
                          double, float2*, double*, long long, int, float2*, float2*, const long long*);
 
-template <int NA>
+template <int NA, bool STAGED>
 KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
   if (vec == 2) {
-    if (two_hops) return has_rot ? estimate_kernel<NA, 2, true, true> : estimate_kernel<NA, 2, true, false>;
-    return has_rot ? estimate_kernel<NA, 2, false, true> : estimate_kernel<NA, 2, false, false>;
+    if (two_hops) return has_rot ? estimate_kernel<NA, 2, true, true, STAGED> : estimate_kernel<NA, 2, true, false, STAGED>;
+    return has_rot ? estimate_kernel<NA, 2, false, true, STAGED> : estimate_kernel<NA, 2, false, false, STAGED>;
   }
-  if (two_hops) return has_rot ? estimate_kernel<NA, 1, true, true> : estimate_kernel<NA, 1, true, false>;
-  return has_rot ? estimate_kernel<NA, 1, false, true> : estimate_kernel<NA, 1, false, false>;
+  if (two_hops) return has_rot ? estimate_kernel<NA, 1, true, true, STAGED> : estimate_kernel<NA, 1, true, false, STAGED>;
+  return has_rot ? estimate_kernel<NA, 1, false, true, STAGED> : estimate_kernel<NA, 1, false, false, STAGED>;
 }
 
 KernelFn pick_kernel(const PlanDev& v) {
-  const bool rot = v.cfo_compensate && v.cfo_defined;
-  return v.est_threads == 512 ? pick_kernel_na<512>(v.vec, v.n_hops == 2, rot) : pick_kernel_na<256>(v.vec, v.n_hops == 2, rot);
+  const bool rot = v.cfo_compensate && v.cfo_defined, two = v.n_hops == 2;
+  if (v.y_bufs == 0) return pick_kernel_na<512, false>(v.vec, two, rot);    // the planner pairs the unstaged layout with NA = 512
+  return v.est_threads == 512 ? pick_kernel_na<512, true>(v.vec, two, rot) : pick_kernel_na<256, true>(v.vec, two, rot);
 }
 
 // Ablation switch for profiling only (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B, bit 2 skips
@@ -1039,7 +1044,7 @@ int upload_plan(Plan& p, std::string& err) {
     return SRSCE_ERR_CUDA;
   }
   int per_sm = 0, sms = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), cta_threads(p.dev.est_threads), p.dev.smem_bytes)) != cudaSuccess ||
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), cta_threads(p.dev.est_threads, p.dev.n_hops == 2), p.dev.smem_bytes)) != cudaSuccess ||
       (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
     err = cuda_msg("occupancy query", e);
     return SRSCE_ERR_CUDA;
@@ -1070,7 +1075,7 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   KernelFn fn = pick_kernel(p.dev);
   const long long cap = (long long)p.n_sms * p.ctas_per_sm;
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
-  fn<<<grid, cta_threads(p.dev.est_threads), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+  fn<<<grid, cta_threads(p.dev.est_threads, p.dev.n_hops == 2), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
       debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact),

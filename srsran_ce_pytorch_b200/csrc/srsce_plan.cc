@@ -442,13 +442,13 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   // shared memory: smoothed pilots of every hop (x hall_bufs) | staged pilot REs (x y_bufs) | raw pilots +
   // virtual pilots, later FFT scratch | the writer warps' expansion tiles | small tables.
   // The planner walks a short list of layouts and takes the first that fits its budget:
-  //   A  two CTAs of 256 estimator threads (+6 writer warps) per SM, pilot REs fetched a whole unit ahead.  The
+  //   A  two CTAs of 256 estimator threads (+4 writer warps) per SM, pilot REs fetched a whole unit ahead.  The
   //      two-CTA footprint is held under the 196 KB carve-out (1 KB per CTA is reserved by the system): one
   //      step higher leaves 28 KB instead of 60 KB of L1 for phase A's twiddle / pilot loads, measured to cost
   //      11 % of the headline throughput.
   //   B  the same CTA shape with a slimmer footprint: one staging buffer (the next unit's pilot REs are fetched
   //      while the IFFT runs), FIR input one CDM group at a time, IFFT two layers at a time.
-  //   C  one CTA of 512 estimator threads (+8 writer warps), one staging buffer, FIR input for all layers (the
+  //   C  one CTA of 512 estimator threads (+6 writer warps), one staging buffer, FIR input for all layers (the
   //      stretch between "writers done" and "next FIR done" is shortest when both CDM groups are de-spread ahead).
   //   D  the same with the slim footprint (the largest geometries).
   //   E  D without a staging buffer: the pilot REs are read from the received grid where they are used (dense
@@ -470,7 +470,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       v.ext_hop = fir_len * ext_layers;                              // FIR input incl. virtual pilots and zero margins, per hop
       int ext = n_hops * v.ext_hop;                                 // (also the scratch of the CNN blend: N * layers <= ext_hop)
       ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
-      const int tile_elems = writer_warps(na) * kTileRows * L * n_hops;
+      const int tile_elems = writer_warps(na, n_hops == 2) * kTileRows * L * n_hops;
       v.ext_elems = ext;
       v.est_threads = na;
       v.hall_bufs = hall_bufs;
@@ -484,13 +484,20 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       return v.smem_bytes;
     };
     const int two_cta_budget = 196 * 1024 / 2 - 1024, one_cta_l1_budget = 196 * 1024 - 1024;
-    (void)one_cta_l1_budget;
-    if (layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
+    // Light phase A (one hop, one pilot symbol, a regular comb) with the vectorised writer (even layer count): one
+    // CTA of 512 + 6 warps beats two of 256 + 4 (C before A; config 2: 0.880 vs 0.852, 2 layers 0.86 vs 0.81, narrow
+    // hops +3 %).  With more pilot symbols, two hops, odd layer counts or a 4096-point IFFT the two-CTA shapes win
+    // (0.75 vs 0.73, 0.69 vs 0.64, 0.80 vs 0.78, 0.52 vs 0.50): their phase A is long enough that a single CTA's
+    // writers starve between hand-overs.
+    const bool light = n_hops == 1 && s_total == 1 && L % 2 == 0 && v.fft_regular;
+    if (!(light && layout(512, 1, 1, false) <= one_cta_l1_budget) &&
+        layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
         layout(512, 1, 1, false) > 227 * 1024 && layout(512, 1, 1, true) > 227 * 1024)
       layout(512, 1, 0, true);
     if (const char* e = getenv("SRSCE_DEBUG_LAYOUT")) {       // experiments only: "na,hall_bufs,y_bufs,slim"
       int na = 256, hb = 1, yb = 2, sl = 0;
-      if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512)) layout(na, hb, yb, sl != 0);
+      if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512))
+        layout(yb == 0 ? 512 : na, hb, yb, sl != 0);              // (the unstaged kernels exist for NA = 512 only)
     }
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);

@@ -297,3 +297,24 @@ def test_indexed_received_grids_equal_materialised_copies():
     assert torch.equal(a, b) and torch.equal(sa, sb)
     with pytest.raises(IndexError):
         plan.estimate_indexed(grids, idx + 1, data["pilots"], 1.0, 4)
+
+
+def test_host_pipeline_matches_device_path():
+    """hostio.HostPipeline (pinned host buffers in / out, two streams) returns what Plan.estimate computes, for the
+    dense and the compact output, including a last partial chunk."""
+    from srsran_ce_pytorch_b200 import estimator
+    from srsran_ce_pytorch_b200.hostio import HostPipeline
+    hop1, hop2, cfg, data = _config2(40, syms=(3, 10))
+    plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    dense, sc = plan.estimate(data["rx"], data["pilots"], 1.0, 4)
+    h_rx, h_pil = data["rx"].cpu().pin_memory(), data["pilots"].cpu().pin_memory()
+    h_out = torch.empty(dense.shape, dtype=torch.complex64).pin_memory()
+    h_sc = torch.empty(sc.shape, dtype=torch.float64).pin_memory()
+    pipe = HostPipeline(plan, 16, 4)
+    pipe.run(h_rx, h_pil, 1.0, h_out, h_sc)
+    assert torch.equal(h_out, dense.cpu()) and torch.equal(h_sc, sc.cpu())
+    assert pipe.launches == 3 and pipe.d2h_bytes == dense.numel() * 8 + 40 * 48
+    ch, rot, _ = plan.estimate_compact(data["rx"], data["pilots"], 1.0, 4)
+    hc = (torch.empty(ch.shape, dtype=torch.complex64).pin_memory(), torch.empty(rot.shape, dtype=torch.complex64).pin_memory())
+    HostPipeline(plan, 16, 4, compact=True).run(h_rx, h_pil, 1.0, hc, h_sc)
+    assert torch.equal(hc[0], ch.cpu()) and torch.equal(hc[1], rot.cpu()) and torch.equal(h_sc, sc.cpu())
