@@ -336,10 +336,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
       float2* const d0 = dst + G * N * H.pilot_col0;
+      // neighbouring threads fetch neighbouring subcarriers (the CDM groups interleave in frequency), so that the
+      // 64-byte fills of one warp walk the grid in address order
       for (int k = tid; k < G * N; k += kThreads) {
-        const int g = (k >= N) ? 1 : 0, i = k - g * N;
+        const int g = (G == 2) ? (k & 1) : 0, i = (G == 2) ? (k >> 1) : k;
         const float2* src = rxn + (long long)pilot_sc(m, H.band_sc0, R, g, i) * ssc;
-        for (int s = 0; s < H.n_dmrs; ++s) cp_async8(d0 + k * H.n_dmrs + s, src + (long long)H.sym_idx[s] * ssym);
+        float2* const d = d0 + (g * N + i) * H.n_dmrs;
+        for (int s = 0; s < H.n_dmrs; ++s) cp_async8(d + s, src + (long long)H.sym_idx[s] * ssym);
       }
     }
     const char* pn = reinterpret_cast<const char*>(pilots + (un / pilot_share) * ((long long)N * ST * L));
