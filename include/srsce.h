@@ -142,7 +142,9 @@ int srsce_estimate_compact(const srsce_plan* plan, const void* rx_grid, const in
 /* srsce_estimate with an indirection on the received grid: unit u reads grid rx_index[u] (a device array of
  * n_units int64), located at rx_grids + rx_index[u]*rx_strides[0].  This is how a caller of the reference
  * passes the SAME received grid to several calls (all UEs multiplexed on one rx antenna in one slot) without
- * materialising copies; the grid is then read from HBM once and from L2 afterwards. */
+ * materialising copies; the grid is then read from HBM once and from L2 afterwards.  (A plan may run a different
+ * CTA shape for this entry point and for srsce_estimate_compact than for srsce_estimate: the channel grids are
+ * bit-identical, the scalars agree to float32 summation order.) */
 int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const int64_t rx_strides[3],
                            const int64_t* rx_index, const void* pilots, int32_t pilot_share, double beta,
                            void* ch_est, double* scalars, int64_t n_units, void* stream);

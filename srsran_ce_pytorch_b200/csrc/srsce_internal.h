@@ -101,7 +101,9 @@ struct PlanDev {
 
 struct Plan {
   srsce_plan_desc desc;
-  PlanDev dev;
+  PlanDev dev;                        // layout for the reference call shape (dense output, one received grid per unit)
+  PlanDev dev_pair;                   // CTA-pair layout of the same plan (valid when has_pair): launches whose pilot
+  bool has_pair = false;              //   gather is cheap -- shared or symbol-major grids -- and the compact output
   std::vector<double> taps;
   std::vector<int32_t> fill_idx;      // host copy of the operator (lerp rows too, for the tests)
   std::vector<float> fill_coef;
@@ -109,6 +111,7 @@ struct Plan {
   int band_rows = 0;
   int device = -1;                    // CUDA device the tables live on, -1: host-only plan
   int ctas_per_sm = 0;                // occupancy of the selected kernel variant
+  int ctas_per_sm_pair = 0;
   int n_sms = 0;
   void* d_twiddle = nullptr;
   void* d_fill_idx = nullptr;

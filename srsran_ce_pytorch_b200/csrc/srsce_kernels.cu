@@ -1039,21 +1039,33 @@ int upload_plan(Plan& p, std::string& err) {
     p.dev.fill_idx = static_cast<const int32_t*>(p.d_fill_idx);
     p.dev.fill_coef = static_cast<const float*>(p.d_fill_coef);
   }
-  KernelFn fn = pick_kernel(p.dev);
-  // the limit is per kernel variant, not per plan: always raise it to the architectural maximum so that
-  // plans with different footprints can share a variant
-  if ((e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem())) != cudaSuccess) {
-    err = cuda_msg("cudaFuncSetAttribute(smem)", e);
+  int sms = 0;
+  if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
+    err = cuda_msg("cudaDeviceGetAttribute", e);
     return SRSCE_ERR_CUDA;
   }
-  int per_sm = 0, sms = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), cta_threads(p.dev.est_threads, p.dev.n_hops == 2), p.dev.smem_bytes)) != cudaSuccess ||
-      (e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) {
-    err = cuda_msg("occupancy query", e);
-    return SRSCE_ERR_CUDA;
+  auto prepare = [&](const PlanDev& v, int* per_sm) -> int {
+    KernelFn fn = pick_kernel(v);
+    // the limit is per kernel variant, not per plan: always raise it to the architectural maximum so that
+    // plans with different footprints can share a variant
+    if ((e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem())) != cudaSuccess) {
+      err = cuda_msg("cudaFuncSetAttribute(smem)", e);
+      return SRSCE_ERR_CUDA;
+    }
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, reinterpret_cast<const void*>(fn), cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes)) != cudaSuccess) {
+      err = cuda_msg("occupancy query", e);
+      return SRSCE_ERR_CUDA;
+    }
+    if (*per_sm < 1) { err = "fused kernel does not fit on an SM"; return SRSCE_ERR_UNSUPPORTED; }
+    return SRSCE_OK;
+  };
+  if (int rc = prepare(p.dev, &p.ctas_per_sm)) return rc;
+  if (p.has_pair) {
+    p.dev_pair.twiddle = p.dev.twiddle;
+    p.dev_pair.fill_idx = p.dev.fill_idx;
+    p.dev_pair.fill_coef = p.dev.fill_coef;
+    if (int rc = prepare(p.dev_pair, &p.ctas_per_sm_pair)) return rc;
   }
-  if (per_sm < 1) { err = "fused kernel does not fit on an SM"; return SRSCE_ERR_UNSUPPORTED; }
-  p.ctas_per_sm = per_sm;
   p.n_sms = sms;
   p.device = dev;
   return SRSCE_OK;
@@ -1075,11 +1087,16 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   cudaGetDevice(&dev);
   if (dev != p.device) { err = "plan was created on another CUDA device"; return SRSCE_ERR_INVALID; }
   if (n_units == 0) return SRSCE_OK;
-  KernelFn fn = pick_kernel(p.dev);
-  const long long cap = (long long)p.n_sms * p.ctas_per_sm;
+  // the reference call shape (dense output, one [n_sc, n_sym] grid per unit) runs the plan's primary layout;
+  // shared grids, other strides and the compact output run the CTA pair when the plan has one
+  const bool reference_shape = rx_index == nullptr && out_compact == nullptr && strides[2] == 1;
+  const bool pair = p.has_pair && !reference_shape;
+  const PlanDev& v = pair ? p.dev_pair : p.dev;
+  KernelFn fn = pick_kernel(v);
+  const long long cap = (long long)p.n_sms * (pair ? p.ctas_per_sm_pair : p.ctas_per_sm);
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
-  fn<<<grid, cta_threads(p.dev.est_threads, p.dev.n_hops == 2), p.dev.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-      p.dev, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
+  fn<<<grid, cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      v, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
       debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact),
       reinterpret_cast<const long long*>(rx_index));

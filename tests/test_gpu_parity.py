@@ -294,7 +294,11 @@ def test_indexed_received_grids_equal_materialised_copies():
     idx = (torch.arange(32, device="cuda") % 4).to(torch.int64)  # ... shared by the 8 UEs (unit = ue * 4 + antenna)
     a, sa = plan.estimate_indexed(grids, idx, data["pilots"], 1.0, 4)
     b, sb = plan.estimate(grids[idx].contiguous(), data["pilots"], 1.0, 4)
-    assert torch.equal(a, b) and torch.equal(sa, sb)
+    # The grids are bit-identical.  The scalars are float32 partial sums per estimator thread combined in float64, and
+    # the shared-grid launch runs the plan's CTA-pair layout (256 estimator threads) where the per-unit-grid launch runs
+    # 512: the summation order differs, so they agree to float32 rounding, not bitwise.
+    assert torch.equal(a, b)
+    assert torch.allclose(sa, sb, rtol=2e-6, atol=1e-12)
     with pytest.raises(IndexError):
         plan.estimate_indexed(grids, idx + 1, data["pilots"], 1.0, 4)
 
