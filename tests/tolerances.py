@@ -15,6 +15,28 @@ CFO_REL, CFO_ABS_OF_SCS = 1e-4, 1e-7
 TA_TIE_MARGIN = 1e-5     # TA must match exactly unless the two largest profile bins are this close
 
 
+def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter"):
+    """NMSE gate for one geometry.  With CFO compensation the reference extrapolates the phase measured between the
+    first two pilot symbols of a hop (float32 correlation sum, float32 angle) over the whole slot: an angle error d
+    becomes a rotation error d * (t - t0) / (t1 - t0), up to 13 / (t1 - t0) symbols of lever.  Different float32
+    summation orders (numpy's pairwise sum vs the kernel's per-thread partial sums) move the angle by ~1e-7 rad, so for
+    adjacent pilot symbols the grid NMSE floor is ~1e-11, not 1e-12 (seen in 4 of 400 random geometries, all with
+    pilot symbols 1-2 apart; perturbing the oracle's own float32 angles by one ulp moves its grid by 3e-13 there).
+    The max-relative-error gate (GRID_MAX_REL) is never widened."""
+    gate = GRID_NMSE
+    if smoothing == "mean":
+        # the whole band collapses to the float32 mean of N pilots whose phases rotate across the band: the mean can
+        # be ~10x smaller than its terms, and numpy's pairwise sum vs the kernel's per-thread partial sums then differ
+        # by ~1e-6 of it (1 of 1200 random geometries: constant error 9e-8 on a layer of mean magnitude 0.05)
+        gate = 10.0 * GRID_NMSE
+    if cfo_compensate:
+        for syms in pilot_symbols_per_hop:
+            if syms is not None and len(syms) >= 2:
+                lever = 13.0 / float(syms[1] - syms[0])
+                gate = max(gate, GRID_NMSE * lever * lever / 4.0)
+    return gate
+
+
 def grid_errors(got, ref):
     got = np.asarray(got)
     ref = np.asarray(ref)
