@@ -261,7 +261,7 @@ def test_short_and_odd_grids_match_oracle(case, two_hops):
                               "unstaged-dense-S2", "unstaged-341prb-S4"])
 def test_persistent_loop_full_band_layouts(pattern, syms, n_units, grid):
     """Full-band geometries that select the other shared-memory layouts (single staging buffer, per-group FIR
-    input, one 768-thread CTA per SM), with more units than resident CTAs so that every CTA pipelines several."""
+    input, one 704-thread CTA per SM), with more units than resident CTAs so that every CTA pipelines several."""
     from srsran_ce_pytorch_b200 import estimator, synth
     hop1 = synth.make_hop(grid, 0, grid, syms, pattern, 2)
     cfg = synth.make_config(30e3, "filter", True)
