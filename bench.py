@@ -37,25 +37,30 @@ UNIT = "estimates/s"
 N_PRB, N_SYM, LAYERS, RX_ANT, UES, PILOT_SYMBOLS = 273, 14, 4, 4, 64, (13,)
 UNITS_PER_SLOT = RX_ANT * UES
 WORKLOAD = "config2"
+FILL = "linear"          # "cnn": the ce_dl_cnn fill + blend (BASELINE configs[3])
 
 
 def select_workload(name, slots):
     """config2 (headline): 4 rx x 64 UEs per slot.  config3: massive-MIMO, 64 rx x 128 UEs per slot
     (BASELINE.json configs[2]; its 1024 slots are streamed `slots` at a time through one reused output buffer)."""
-    global RX_ANT, UES, UNITS_PER_SLOT, WORKLOAD
+    global RX_ANT, UES, UNITS_PER_SLOT, WORKLOAD, FILL
     WORKLOAD = name
     if name == "config3":
         RX_ANT, UES = 64, 128
+    if name == "config4":                      # ce_dl_cnn on the config-2 geometry, 4096 UE-antenna grids per step
+        FILL = "cnn"
     UNITS_PER_SLOT = RX_ANT * UES
-    return slots if slots else (64 if name == "config2" else 2)
+    return slots if slots else {"config2": 64, "config3": 2, "config4": 16}[name]
 
 
 def workload_config(slots, e2e_slots=None):
-    cfg = {"workload": f"{WORKLOAD}: ce_rule_tensorized batched, 273 PRB 30 kHz, 4 ports, {RX_ANT} rx antennas, comb-4, "
+    variant = "ce_dl_cnn (inpainting fill + blend)" if FILL == "cnn" else "ce_rule_tensorized"
+    cfg = {"workload": f"{WORKLOAD}: {variant} batched, 273 PRB 30 kHz, 4 ports, {RX_ANT} rx antennas, comb-4, "
                        f"{UES} UEs per slot, 1 pilot symbol, 14-symbol grid, filter smoothing, CFO compensation on",
            "units_per_step_per_gpu": slots * UNITS_PER_SLOT, "slots_per_step_per_gpu": slots, "estimates_per_unit": LAYERS,
            "rx_layout": "reference ([n_sc, n_sym] row major per unit, one grid per unit)",
-           "l2_policy": "inputs+outputs per step (>= 7 GB) exceed the 126 MB L2; no flush needed"}
+           "l2_policy": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed"
+                        % (slots * UNITS_PER_SLOT * (algorithmic_bytes_per_unit() + 12 * N_PRB * N_SYM * 8) / 1e9)}
     if e2e_slots is not None:
         cfg["e2e_units_per_step"] = min(e2e_slots * UNITS_PER_SLOT, slots * UNITS_PER_SLOT, 2048)
     return cfg
@@ -83,10 +88,13 @@ def cpu_pool(n_distinct=None):
     n_distinct = n_distinct or max(16, RX_ANT)
     d = synth.make_units(hop1, hop2, cfg, LAYERS, n_distinct, pilot_share=RX_ANT, seed=4321)
     return cpu_bench.OraclePool(d["rx"].numpy(), d["pilots"].numpy(), RX_ANT, 1.0, ce_oracle.hop_from_any(hop1),
-                                ce_oracle.HopSpec.absent(), ce_oracle.est_from_any(cfg))
+                                ce_oracle.HopSpec.absent(), ce_oracle.est_from_any(cfg),
+                                fill="cnn" if FILL == "cnn" else "tensorized")
 
 
 def cpu_baseline(units_per_worker=480):
+    if FILL == "cnn":
+        units_per_worker = 48                      # the port of ce_dl_cnn's inpainting loop takes ~0.2 s per unit
     pool = cpu_pool()
     try:
         pool.run(4)
@@ -96,8 +104,9 @@ def cpu_baseline(units_per_worker=480):
     units = pool.cores * units_per_worker
     return {"value": LAYERS * units / wall, "unit": UNIT, "cores": pool.cores, "kind": "port",
             "sample": f"{units} units of the bench workload ({units_per_worker} per worker, 1 thread each, "
-                      f"{wall:.2f} s wall); numpy port of ce_rule_tensorized (2.9x faster than the torch "
-                      f"reference in the build container)"}
+                      f"{wall:.2f} s wall); numpy port of " +
+                      ("ce_dl_cnn" if FILL == "cnn" else "ce_rule_tensorized (2.9x faster than the torch reference in the "
+                                                         "build container)")}
 
 
 def run_reference(args):
@@ -105,7 +114,7 @@ def run_reference(args):
     if rank != 0:
         return
     pool = cpu_pool()
-    upw = 96                                      # units per worker and step: 1536 units per step on 16 cores, ~0.2 s
+    upw = 8 if FILL == "cnn" else 96              # units per worker and step: 1536 units per step on 16 cores, ~0.2 s
     try:
         for _ in range(max(1, args.warmup)):
             pool.run(4)
@@ -227,7 +236,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     hop1, hop2, cfg = geometry()
-    plan = estimator.make_plan(N_PRB, N_SYM, LAYERS, hop1, hop2, cfg)
+    plan = estimator.make_plan(N_PRB, N_SYM, LAYERS, hop1, hop2, cfg, FILL)
     n_local = args.slots * UNITS_PER_SLOT
     n_global = n_local * world
     rx, pil = make_step_inputs(args.slots, 1234 + 1000 * rank, dev)
@@ -434,8 +443,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--slots", type=int, default=0, help="slots per step and per GPU (default: 64 for config2, 2 for config3)")
-    ap.add_argument("--workload", choices=["config2", "config3"], default="config2")
+    ap.add_argument("--slots", type=int, default=0, help="slots per step and per GPU (default: 64 for config2, 2 for config3, 16 for config4)")
+    ap.add_argument("--workload", choices=["config2", "config3", "config4"], default="config2")
     ap.add_argument("--e2e-slots", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

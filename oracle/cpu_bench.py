@@ -17,11 +17,12 @@ import numpy as np
 _STATE = {}
 
 
-def _init(rx, pilots, share, beta, hop1, hop2, cfg):
+def _init(rx, pilots, share, beta, hop1, hop2, cfg, fill="tensorized"):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import ce_oracle
-    _STATE.update(rx=rx, pilots=pilots, share=share, beta=beta, hop1=hop1, hop2=hop2, cfg=cfg, est=ce_oracle.estimate)
-    ce_oracle.estimate(rx[0], pilots[0], beta, hop1, hop2, cfg)      # warm caches / imports
+    _STATE.update(rx=rx, pilots=pilots, share=share, beta=beta, hop1=hop1, hop2=hop2, cfg=cfg, fill=fill,
+                  est=ce_oracle.estimate)
+    ce_oracle.estimate(rx[0], pilots[0], beta, hop1, hop2, cfg, fill=fill)      # warm caches / imports
 
 
 def _work(args):
@@ -31,7 +32,7 @@ def _work(args):
     acc = 0.0
     for k in range(first, first + count):
         b = k % n
-        out = s["est"](s["rx"][b], s["pilots"][b // s["share"]], s["beta"], s["hop1"], s["hop2"], s["cfg"])
+        out = s["est"](s["rx"][b], s["pilots"][b // s["share"]], s["beta"], s["hop1"], s["hop2"], s["cfg"], fill=s["fill"])
         acc += float(out[2])
     return acc
 
@@ -40,11 +41,11 @@ class OraclePool:
     """``cores`` single-threaded workers, each holding the same small set of distinct units."""
 
     def __init__(self, rx: np.ndarray, pilots: np.ndarray, share: int, beta: float, hop1, hop2, cfg,
-                 cores: int | None = None):
+                 cores: int | None = None, fill: str = "tensorized"):
         import multiprocessing as mp
         self.cores = cores or len(os.sched_getaffinity(0))
         ctx = mp.get_context("spawn")
-        self.pool = ctx.Pool(self.cores, initializer=_init, initargs=(rx, pilots, share, beta, hop1, hop2, cfg))
+        self.pool = ctx.Pool(self.cores, initializer=_init, initargs=(rx, pilots, share, beta, hop1, hop2, cfg, fill))
         self.pool.map(_work, [(0, 1)] * self.cores)                  # every worker is up and warm
 
     def run(self, units_per_worker: int) -> float:
