@@ -48,7 +48,7 @@ struct Misc {
   double taps[SRSCE_MAX_TAPS + 1];
   LerpEntry lerp[2][kNRE];
   int32_t re_pos[2][kNRE];
-  unsigned long long r_magic;
+  unsigned int r_magic, r_magic_pad;
   float cnn_coef[2][kNRE][kMaxFillTerms];
   int32_t cnn_idx0[2][kNRE];
   ColInfo col[2][SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];   // one store-slot table per hall buffer
@@ -107,9 +107,11 @@ __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
 }
 
 // Subcarrier of pilot i of CDM group g inside a hop band.
-// (i / R by multiply-shift: r_magic = ceil(2^32 / R) is exact for i < 2^16, R <= 12)
+// (i / R as one IMAD.HI: r_magic = ceil(2^32 / R) is exact for i < 2^16, 2 <= R <= 12; R == 1 has no 32-bit magic.
+//  Written with __umulhi on purpose: the 64-bit form `(u64(i) * magic) >> 32` followed by `q * R` was mis-folded by
+//  ptxas 12.9 in one instantiation -- it reassociated to i * hi32(magic * R) -- and faulted)
 __device__ __forceinline__ int pilot_sc(const Misc& m, int band_sc0, int R, int g, int i) {
-  const int q = int((static_cast<unsigned long long>(static_cast<unsigned>(i)) * m.r_magic) >> 32);
+  const int q = (R == 1) ? i : int(__umulhi(static_cast<unsigned>(i), m.r_magic));
   return band_sc0 + q * kNRE + m.re_pos[g][i - q * R];
 }
 
@@ -322,7 +324,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     m.re_pos[k / kNRE][k % kNRE] = P.re_pos[k / kNRE][k % kNRE];
     m.cnn_idx0[k / kNRE][k % kNRE] = P.cnn_idx0[k / kNRE][k % kNRE];
   }
-  if (tid == 0) m.r_magic = ((1ull << 32) + static_cast<unsigned>(R) - 1) / static_cast<unsigned>(R);
+  if (tid == 0) m.r_magic = (R == 1) ? 0u : static_cast<unsigned>(((1ull << 32) + static_cast<unsigned>(R) - 1) / static_cast<unsigned>(R));
   for (int k = tid; k < 2 * kNRE * kMaxFillTerms; k += kThreads)
     (&m.cnn_coef[0][0][0])[k] = (&P.cnn_coef[0][0][0])[k];
   __syncthreads();
@@ -331,7 +333,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   // ================================ estimator warps ==========================================
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
-    if ((!STAGED && P.y_bufs == 0) || un >= n_units || (dbg & 4)) return;          // (unstaged fallback / ablation bit 2: no staging traffic)
+    if (!STAGED || un >= n_units || (dbg & 4)) return;          // (unstaged fallback / ablation bit 2: no staging traffic)
     const float2* rxn = rx + (rx_index ? __ldg(rx_index + un) : un) * su;     // several units may share one received grid
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
@@ -390,10 +392,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     // that the staged variants do not carry its address arithmetic) -- straight from the received grid
     const float2* const rxu = STAGED ? rx : rx + (rx_index ? __ldg(rx_index + u) : u) * su;
     auto ld_y = [&](const HopDev& H, int g, int i, int s) -> float2 {
-      // (the unstaged instantiation keeps the run-time test as well: with the shared-memory path compiled out, the
-      //  nvcc 12.9 build of this lambda faulted with an illegal address on B200 whenever a hop has two pilot symbols;
-      //  not understood -- DESIGN.md section 7)
-      if (STAGED || P.y_bufs != 0) return ys[G * N * H.pilot_col0 + (g * N + i) * H.n_dmrs + s];
+      if (STAGED) return ys[G * N * H.pilot_col0 + (g * N + i) * H.n_dmrs + s];
       return __ldg(rxu + (long long)pilot_sc(m, H.band_sc0, R, g, i) * ssc + (long long)H.sym_idx[s] * ssym);
     };
     const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
