@@ -322,3 +322,17 @@ def test_host_pipeline_matches_device_path():
     hc = (torch.empty(ch.shape, dtype=torch.complex64).pin_memory(), torch.empty(rot.shape, dtype=torch.complex64).pin_memory())
     HostPipeline(plan, 16, 4, compact=True).run(h_rx, h_pil, 1.0, hc, h_sc)
     assert torch.equal(hc[0], ch.cpu()) and torch.equal(hc[1], rot.cpu()) and torch.equal(h_sc, sc.cpu())
+
+
+@pytest.mark.parametrize("syms", [(13,), (3, 10)], ids=["single-cta", "cta-pair"])
+def test_unit_counts_around_the_resident_cta_count(syms):
+    """Launches of 1 ... 2 x SMs + 1 units: grids smaller than, equal to and just above the number of resident CTAs
+    (one per SM for the single-CTA layout, two for the pair) give the same per-unit results as one large launch."""
+    from srsran_ce_pytorch_b200 import estimator
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    hop1, hop2, cfg, data = _config2(2 * n_sm + 4, syms=syms)
+    plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    full, sc_full = plan.estimate(data["rx"], data["pilots"], 1.0, 4)
+    for n in (4, n_sm - 4, n_sm, n_sm + 4, 2 * n_sm - 4, 2 * n_sm, 2 * n_sm + 4):
+        out, sc = plan.estimate(data["rx"][:n], data["pilots"][:n // 4], 1.0, 4)
+        assert torch.equal(out, full[:n]) and torch.equal(sc, sc_full[:n]), n
