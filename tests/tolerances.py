@@ -15,7 +15,7 @@ CFO_REL, CFO_ABS_OF_SCS = 1e-4, 1e-7
 TA_TIE_MARGIN = 1e-5     # TA must match exactly unless the two largest profile bins are this close
 
 
-def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter"):
+def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_pilots=None):
     """NMSE gate for one geometry.  With CFO compensation the reference extrapolates the phase measured between the
     first two pilot symbols of a hop (float32 correlation sum, float32 angle) over the whole slot: an angle error d
     becomes a rotation error d * (t - t0) / (t1 - t0), up to 13 / (t1 - t0) symbols of lever.  Different float32
@@ -29,6 +29,11 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter"):
         # be ~10x smaller than its terms, and numpy's pairwise sum vs the kernel's per-thread partial sums then differ
         # by ~1e-6 of it (1 of 1200 random geometries: constant error 9e-8 on a layer of mean magnitude 0.05)
         gate = 10.0 * GRID_NMSE
+    if smoothing == "filter" and n_pilots is not None and n_pilots <= 12:
+        # every output sits next to the virtual pilots, which extrapolate float32 `angle` values (CUDA atan2f: <= 2 ulp,
+        # numpy: correctly rounded) -- one ulp of angle noise moves the oracle's own grid by 3e-13 here, two by 1.2e-12
+        # (1 of 3 200 random geometries: 3 pilots per hop, NMSE 1.19e-12)
+        gate = max(gate, 4.0 * GRID_NMSE)
     if cfo_compensate:
         for syms in pilot_symbols_per_hop:
             if syms is not None and len(syms) >= 2:
