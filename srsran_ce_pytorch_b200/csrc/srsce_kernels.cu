@@ -63,6 +63,36 @@ struct HopScratch {        // per hop, after Misc
 static_assert(sizeof(HopScratch) <= kHopScratchBytes, "HopScratch does not fit its shared-memory slot");
 static_assert(sizeof(Misc) <= kMiscBytes, "Misc does not fit its shared-memory slot");
 
+// Profiling build only (make prof -> libsrsce_prof.so, used by tools/): ablation switches and per-section cycle
+// counters.  The production library has neither: `dbg` is a compile-time 0 and PROF_MARK expands to nothing.
+#ifdef SRSCE_PROFILING
+constexpr int kProfSlots = 16;
+__device__ long long* g_prof_buf = nullptr;       // [gridDim.x][kProfSlots] cycles, set by srsce_prof_set_buffer
+// Attribute the cycles since the previous mark of this thread to section k.  The shared-memory read makes the
+// thread really wait for a preceding bar.sync (BAR.SYNC.DEFER_BLOCKING lets the clock read run ahead otherwise).
+#define PROF_DECL long long prof_acc[kProfSlots] = {0}; long long prof_t = clock64();
+#define PROF_MARK(cond, k)                                                                          \
+  do {                                                                                              \
+    if (cond) {                                                                                     \
+      unsigned prof_dummy;                                                                          \
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(prof_dummy) : "r"((unsigned)__cvta_generic_to_shared(smem)) : "memory"); \
+      const long long prof_now = clock64();                                                         \
+      prof_acc[k] += prof_now - prof_t + (prof_dummy & 0);                                          \
+      prof_t = prof_now;                                                                            \
+    }                                                                                               \
+  } while (0)
+#define PROF_FLUSH(cond, base)                                                                      \
+  do {                                                                                              \
+    if ((cond) && g_prof_buf != nullptr)                                                            \
+      for (int k_ = 0; k_ < kProfSlots; ++k_)                                                       \
+        if (prof_acc[k_]) g_prof_buf[(long long)blockIdx.x * kProfSlots + k_] = prof_acc[k_];       \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(cond, k) do { } while (0)
+#define PROF_FLUSH(cond, base) do { } while (0)
+#endif
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -293,8 +323,13 @@ template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT, bool STAGED>
 __global__ void __launch_bounds__(cta_threads(NA, TWO_HOPS), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
-                float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg,
+                float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg_arg,
                 float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index) {
+#ifdef SRSCE_PROFILING
+  const int dbg = dbg_arg;                                  // ablation bits (profiling build only)
+#else
+  constexpr int dbg = 0;
+#endif
   constexpr int kThreads = NA;                              // estimator threads
   constexpr int kWarpsB = (NA == 256) ? (TWO_HOPS ? 6 : 4) : (TWO_HOPS ? 8 : 6);   // = writer_warps(NA, TWO_HOPS)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
@@ -331,6 +366,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 
   if (tid < kThreads) {
   // ================================ estimator warps ==========================================
+  PROF_DECL
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
     if (!STAGED || un >= n_units || (dbg & 4)) return;          // (unstaged fallback / ablation bit 2: no staging traffic)
@@ -386,6 +422,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
+    PROF_MARK(tid == 0, 0);
     const float2* const ys = ystage + ((P.y_bufs == 2) ? (it & 1) * ylen : 0);
     // received pilot RE (hop H, group g, pilot i, pilot symbol s): from the staged copy, or -- the fallback for
     // geometries whose staging buffer does not fit beside the rest (STAGED = false, a separate instantiation so
@@ -455,12 +492,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
       if (P.cfo_defined) sync_a<NA>();
+      PROF_MARK(tid == 0, 1);
 
       // ---- LS estimate, symbol average, CDM pair average (:593, :613-628) + EPRE (:584), then smoothing
       //      (:633-668).  With the raised-cosine filter the raw pilots go through ext (FIR input, one region
       //      per hop); when the planner asked for it, one CDM group (<= 2 layers) at a time so that ext stays small.
       float epre_part[2] = {0.f, 0.f};
       if (!filt && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // LS writes hall: writers must be done with it
+      PROF_MARK(tid == 0 && !filt, 4);
       const int n_batches = (filt && P.fir_per_group) ? G : 1;
       for (int bt = 0; bt < n_batches; ++bt) {
         const int g_lo = (n_batches == 1) ? 0 : bt, g_hi = (n_batches == 1) ? G : bt + 1;
@@ -525,6 +564,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
         }
         sync_a<NA>();
+        PROF_MARK(tid == 0, 2);
 
         if (filt) {
           if (nv > 0) {
@@ -549,7 +589,9 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           }
           sync_a<NA>();
+          PROF_MARK(tid == 0, 3);
           if (bt == 0 && wait_empty) bar_sync(kBarEmpty + hb_idx, kCtaThreads);   // the FIR overwrites hall: writers must be done with it
+          PROF_MARK(tid == 0, 4);
           // conv(ext, taps, "same") cropped to the real pilots, float64 accumulation (:459-493);
           // two adjacent outputs per thread share all but one of their input samples
 #pragma unroll
@@ -602,6 +644,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
             sync_a<NA>();
           }
+          PROF_MARK(tid == 0, 5);
         }
       }  // group batches
 
@@ -636,9 +679,11 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       // ---- the smoothed pilots of every hop are final: build the store-slot table (final CFO
       //      rotation :922-929, allocation flags) and release the writer warps; the noise estimate and
       //      the time alignment below only read hall, concurrently with them
+      PROF_MARK(tid == 0, 6);
       build_store_table(m.col[hb_idx]);
       write_symbol_rotation(u);
       bar_arrive(kBarFull + hb_idx, kCtaThreads);
+      PROF_MARK(tid == 0, 7);
 
       // ---- reconstruction, noise, RSRP (:701-730)
       {
@@ -688,6 +733,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
       sync_a<NA>();
+      PROF_MARK(tid == 0, 8);
       if (P.y_bufs == 1) {                                      // single staging buffer: this unit's pilot REs are dead now;
         stage_unit(u + gridDim.x, ystage);                     // the next unit's arrive while the IFFT below runs
         cp_async_commit();
@@ -752,6 +798,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
       sync_a<NA>();   // ext (IFFT scratch), the profiles and ta_hop are complete
+      PROF_MARK(tid == 0, 9);
       if (tid == 0) {
 #pragma unroll
         for (int hh = 0; hh < n_hops; ++hh) m.acc[3] += m.ta_hop[hh];
@@ -775,16 +822,19 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     }
     // (the barrier at the top of the next unit orders these reads of m.acc before it is cleared)
   }
+  PROF_FLUSH(tid == 0, 0);
   } else {
   // ================================== writer warps ============================================
   const int wb = warp - NA / 32;
   const long long n_iter = (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   int it = 0;
+  PROF_DECL
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
     const int hb_idx = (P.hall_bufs == 2) ? (it & 1) : 0;
     const float2* const hall = hall0 + hb_idx * (n_hops * L * N);
     const ColInfo* const colb = m.col[hb_idx];
     bar_sync(kBarFull + hb_idx, kCtaThreads);
+    PROF_MARK(wb == 0 && lane == 0, 11);
     // ===================================== phase B ==========================================
     // Each warp takes 32 consecutive subcarriers: lane r interpolates row r into the warp's tile
     // ([hop][row][layer]), then the warp streams the rows out, every lane owning a fixed store
@@ -955,8 +1005,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         }
       }
     }
+    PROF_MARK(wb == 0 && lane == 0, 12);
     if (it + P.hall_bufs < n_iter) bar_arrive(kBarEmpty + hb_idx, kCtaThreads);   // this buffer may be rewritten
   }
+  PROF_FLUSH(wb == 0 && lane == 0, 0);
   }
 }
 
@@ -979,18 +1031,21 @@ KernelFn pick_kernel(const PlanDev& v) {
   return v.est_threads == 512 ? pick_kernel_na<512, true>(v.vec, two, rot) : pick_kernel_na<256, true>(v.vec, two, rot);
 }
 
-// Ablation switch for profiling only (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B, bit 2 skips
-// the staging loads);
-// results are garbage when set, so it is read from the environment and never from the API.
+// Ablation switch, PROFILING BUILD ONLY (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B, bit 2 skips
+// the staging loads): results are garbage when set.  The production library never reads the environment.
+#ifdef SRSCE_PROFILING
 int debug_mode() {
   static const int mode = [] {
     const char* e = getenv("SRSCE_DEBUG_ABLATE");
     const int v = e ? atoi(e) : 0;
-    if (v) fprintf(stderr, "libsrsce: SRSCE_DEBUG_ABLATE=%d -- profiling ablation active, RESULTS ARE INVALID\n", v);
+    if (v) fprintf(stderr, "libsrsce_prof: SRSCE_DEBUG_ABLATE=%d -- profiling ablation active, RESULTS ARE INVALID\n", v);
     return v;
   }();
   return mode;
 }
+#else
+constexpr int debug_mode() { return 0; }
+#endif
 
 std::string cuda_msg(const char* what, cudaError_t e) {
   return std::string(what) + ": " + cudaGetErrorString(e);
@@ -999,6 +1054,14 @@ std::string cuda_msg(const char* what, cudaError_t e) {
 }  // namespace
 
 int max_dynamic_smem() { return 227 * 1024; }   // architectural per-CTA limit on sm_100
+
+#ifdef SRSCE_PROFILING
+// [grid][16] int64 cycle counters per CTA (device memory, zeroed by the caller); nullptr switches them off.
+extern "C" int srsce_prof_set_buffer(void* device_ptr) {
+  long long* p = static_cast<long long*>(device_ptr);
+  return cudaMemcpyToSymbol(g_prof_buf, &p, sizeof p) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int upload_plan(Plan& p, std::string& err) {
   int count = 0;

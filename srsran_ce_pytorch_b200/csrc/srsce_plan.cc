@@ -506,12 +506,14 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       }
       v = primary;
     }
+#ifdef SRSCE_PROFILING
     if (const char* e = getenv("SRSCE_DEBUG_LAYOUT")) {
       p.has_pair = false;       // experiments only: "na,hall_bufs,y_bufs,slim"
       int na = 256, hb = 1, yb = 2, sl = 0;
       if (sscanf(e, "%d,%d,%d,%d", &na, &hb, &yb, &sl) == 4 && (na == 256 || na == 512))
         layout(yb == 0 ? 512 : na, hb, yb, sl != 0);              // (the unstaged kernels exist for NA = 512 only)
     }
+#endif
     if (v.smem_bytes > 227 * 1024)
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }

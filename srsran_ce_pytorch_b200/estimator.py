@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -88,11 +89,16 @@ class Plan:
         _lib.raise_for(lib.srsce_plan_tables(self._h, taps.ctypes.data, idx.ctypes.data, coef.ctypes.data))
         return taps[:i.n_taps], idx, coef
 
-    # ---- the compute call
-    def estimate(self, rx: torch.Tensor, pilots: torch.Tensor, beta: float, pilot_share: int = 1,
-                 out: Optional[torch.Tensor] = None, scalars: Optional[torch.Tensor] = None):
-        """rx [B, n_sc, n_sym] complex64 CUDA (any strides), pilots [B // pilot_share, n_re, S, L]
-        complex64 contiguous.  Returns (ch_est [B, n_sc, n_sym, L], scalars [B, 6] float64)."""
+    # ---- argument checks shared by the compute calls
+    @staticmethod
+    def _materialize(t: torch.Tensor) -> torch.Tensor:
+        """The kernel reads raw storage: lazily conjugated / negated views (``x.conj()`` keeps the storage of
+        ``x`` and only sets a flag) must be resolved before their data_ptr() crosses the ABI."""
+        return t.resolve_conj().resolve_neg()
+
+    def _check_inputs(self, rx, pilots, pilot_share, n_units=None):
+        """rx [*, n_sc, n_sym] (any strides) and pilots [n_units // share, n_re, S, L]; returns
+        (n_units, rx, pilots) with conj/neg views resolved and the pilots contiguous."""
         i = self.info
         if not rx.is_cuda or not pilots.is_cuda:
             raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
@@ -100,23 +106,39 @@ class Plan:
             raise TypeError("rx and pilots must be complex64")
         if rx.dim() != 3 or tuple(rx.shape[1:]) != (i.n_sc, i.n_sym):
             raise IndexError(f"received grid shape {tuple(rx.shape)} != [B, {i.n_sc}, {i.n_sym}]")
-        n_units = int(rx.shape[0])
+        if pilots.device != rx.device:
+            raise RuntimeError("rx and pilots must live on the same CUDA device")
+        n_units = int(rx.shape[0]) if n_units is None else int(n_units)
         if pilot_share < 1 or n_units % pilot_share:
             raise ValueError("number of units must be a multiple of pilot_share")
         want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
         if tuple(pilots.shape) != want:
             raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
-        if not pilots.is_contiguous():
-            pilots = pilots.contiguous()
+        return n_units, self._materialize(rx), self._materialize(pilots).contiguous()
+
+    def _check_outputs(self, n_units, device, out, scalars):
+        """Caller-supplied result buffers are written by the kernel without any further check: shape, dtype,
+        contiguity and device must be exactly what the ABI documents."""
+        i = self.info
         if out is None:
-            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=rx.device)
+            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=device)
         elif tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers) or not out.is_contiguous() \
-                or out.dtype != torch.complex64 or out.device != rx.device:
+                or out.dtype != torch.complex64 or out.device != device or out.is_conj() or out.is_neg():
             raise ValueError("out must be a contiguous complex64 [B, n_sc, n_sym, L] tensor on rx.device")
         if scalars is None:
-            scalars = torch.empty((n_units, 6), dtype=torch.float64, device=rx.device)
-        elif tuple(scalars.shape) != (n_units, 6) or not scalars.is_contiguous() or scalars.dtype != torch.float64:
-            raise ValueError("scalars must be a contiguous float64 [B, 6] tensor")
+            scalars = torch.empty((n_units, 6), dtype=torch.float64, device=device)
+        elif tuple(scalars.shape) != (n_units, 6) or not scalars.is_contiguous() or scalars.dtype != torch.float64 \
+                or scalars.device != device:
+            raise ValueError("scalars must be a contiguous float64 [B, 6] tensor on rx.device")
+        return out, scalars
+
+    # ---- the compute calls
+    def estimate(self, rx: torch.Tensor, pilots: torch.Tensor, beta: float, pilot_share: int = 1,
+                 out: Optional[torch.Tensor] = None, scalars: Optional[torch.Tensor] = None):
+        """rx [B, n_sc, n_sym] complex64 CUDA (any strides), pilots [B // pilot_share, n_re, S, L]
+        complex64.  Returns (ch_est [B, n_sc, n_sym, L], scalars [B, 6] float64)."""
+        n_units, rx, pilots = self._check_inputs(rx, pilots, pilot_share)
+        out, scalars = self._check_outputs(n_units, rx.device, out, scalars)
         strides = (C.c_int64 * 3)(*rx.stride())
         with torch.cuda.device(rx.device):
             stream = torch.cuda.current_stream().cuda_stream
@@ -125,50 +147,23 @@ class Plan:
                                               C.c_void_p(stream)))
         return out, scalars
 
-
-    def _check_inputs(self, rx, pilots, pilot_share):
-        i = self.info
-        if not rx.is_cuda or not pilots.is_cuda:
-            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
-        if rx.dtype != torch.complex64 or pilots.dtype != torch.complex64:
-            raise TypeError("rx and pilots must be complex64")
-        if rx.dim() != 3 or tuple(rx.shape[1:]) != (i.n_sc, i.n_sym):
-            raise IndexError(f"received grid shape {tuple(rx.shape)} != [B, {i.n_sc}, {i.n_sym}]")
-        n_units = int(rx.shape[0])
-        if pilot_share < 1 or n_units % pilot_share:
-            raise ValueError("number of units must be a multiple of pilot_share")
-        want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
-        if tuple(pilots.shape) != want:
-            raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
-        return n_units, (pilots if pilots.is_contiguous() else pilots.contiguous())
-
     def estimate_indexed(self, rx_grids: torch.Tensor, rx_index: torch.Tensor, pilots: torch.Tensor, beta: float,
                          pilot_share: int = 1, out: Optional[torch.Tensor] = None,
-                         scalars: Optional[torch.Tensor] = None):
+                         scalars: Optional[torch.Tensor] = None, check_index: bool = True):
         """Like ``estimate`` but unit u reads received grid ``rx_grids[rx_index[u]]``: the way to hand the same
         grid (one rx antenna, one slot) to the units of every UE multiplexed on it, as a caller of the reference
-        does by passing the same tensor to several calls.  rx_grids [n_grids, n_sc, n_sym]; rx_index int64 [B]."""
-        i = self.info
-        if not rx_grids.is_cuda or not pilots.is_cuda or not rx_index.is_cuda:
-            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
-        if rx_grids.dtype != torch.complex64 or pilots.dtype != torch.complex64 or rx_index.dtype != torch.int64:
-            raise TypeError("rx_grids / pilots must be complex64 and rx_index int64")
-        if rx_grids.dim() != 3 or tuple(rx_grids.shape[1:]) != (i.n_sc, i.n_sym):
-            raise IndexError(f"received grids shape {tuple(rx_grids.shape)} != [G, {i.n_sc}, {i.n_sym}]")
-        n_units = int(rx_index.numel())
-        if pilot_share < 1 or n_units % pilot_share:
-            raise ValueError("number of units must be a multiple of pilot_share")
-        want = (n_units // pilot_share, i.n_re, i.n_dmrs_total, i.n_layers)
-        if tuple(pilots.shape) != want:
-            raise IndexError(f"pilots shape {tuple(pilots.shape)} != {want}")
-        if n_units and (int(rx_index.min()) < 0 or int(rx_index.max()) >= rx_grids.shape[0]):
+        does by passing the same tensor to several calls.  rx_grids [n_grids, n_sc, n_sym]; rx_index int64 [B].
+        ``check_index`` verifies 0 <= rx_index < n_grids, which reads two values back from the device and so
+        synchronises the stream; callers that build the index themselves pass False to stay asynchronous."""
+        if not rx_index.is_cuda or rx_index.device != rx_grids.device:
+            raise RuntimeError("rx_index must live on the CUDA device of rx_grids")
+        if rx_index.dtype != torch.int64 or rx_index.dim() != 1:
+            raise TypeError("rx_index must be a 1-D int64 tensor")
+        n_units, rx_grids, pilots = self._check_inputs(rx_grids, pilots, pilot_share, n_units=rx_index.numel())
+        if check_index and n_units and (int(rx_index.min()) < 0 or int(rx_index.max()) >= rx_grids.shape[0]):
             raise IndexError("rx_index out of range")
-        pilots = pilots if pilots.is_contiguous() else pilots.contiguous()
         rx_index = rx_index.contiguous()
-        if out is None:
-            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=rx_grids.device)
-        if scalars is None:
-            scalars = torch.empty((n_units, 6), dtype=torch.float64, device=rx_grids.device)
+        out, scalars = self._check_outputs(n_units, rx_grids.device, out, scalars)
         strides = (C.c_int64 * 3)(*rx_grids.stride())
         with torch.cuda.device(rx_grids.device):
             stream = torch.cuda.current_stream().cuda_stream
@@ -181,7 +176,7 @@ class Plan:
         """Compact output (not part of the reference contract): returns (ch_sc [B, n_hops, n_sc, L],
         sym_rot [B, n_sym], scalars [B, 6]); ``expand_compact`` rebuilds the dense grid."""
         i = self.info
-        n_units, pilots = self._check_inputs(rx, pilots, pilot_share)
+        n_units, rx, pilots = self._check_inputs(rx, pilots, pilot_share)
         n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
         ch = torch.empty((n_units, n_hops, i.n_sc, i.n_layers), dtype=torch.complex64, device=rx.device)
         rot = torch.empty((n_units, i.n_sym), dtype=torch.complex64, device=rx.device)
@@ -213,12 +208,63 @@ class Plan:
 
 _PLANS: dict = {}
 _PLANS_LOCK = threading.Lock()
+_MEMO: dict = {}                 # (ids of hop1 / hop2 / config, shapes, fill, device) -> (fingerprint, weakrefs, plan)
+_MEMO_MAX = 256
+_HOP_FIELDS = ("DMRSsymbols", "DMRSREmask", "PRBstart", "nPRBs", "maskPRBs", "startSymbol", "nAllocatedSymbols")
+_CFG_FIELDS = ("scs", "CyclicPrefixDurations", "Smoothing", "CFOCompensate", "CNNSmoothingAlpha")
+
+
+def _fingerprint(obj, fields):
+    """Identity + in-place-modification counter of every tensor field, value of every plain field: equal
+    fingerprints of the same (live) object mean its contents have not changed since the plan was made."""
+    out = []
+    for f in fields:
+        v = getattr(obj, f, None)
+        if isinstance(v, torch.Tensor):
+            out.append((id(v), v._version))
+        elif isinstance(v, np.ndarray):
+            return None                                # numpy arrays carry no version counter: never memoised
+        else:
+            out.append(v)
+    return tuple(out)
+
+
+def _device_index(device) -> int:
+    if not torch.cuda.is_available():
+        return -1                                      # host-only plan (CPU-side tests of the planner)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return dev.index if dev.index is not None else torch.cuda.current_device()
 
 
 def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fill: str = "linear",
               device=None) -> Plan:
     """Build (or fetch from the cache) the plan for HopConfig x2 + EstimatorConfig + tensor shapes.
-    A plan's tables live on one CUDA device (``device``, default: the current one); the cache is per device."""
+    A plan's tables live on one CUDA device (``device``, default: the current one); the cache is per device.
+
+    Turning the dataclasses into a descriptor reads their mask tensors on the host (a device->host copy and a
+    stream synchronisation if they live on the GPU, as the reference's own ``.item()`` calls do).  That is done
+    once per (hop1, hop2, config) object: repeated calls with the same, unmodified objects hit a memo keyed on
+    object identity and tensor version counters and touch neither the tensors nor the stream."""
+    dev_index = _device_index(device)
+    memo_key = (id(hop1), id(hop2), id(config), int(n_prb_grid), int(n_sym), int(n_layers), fill, dev_index)
+    fp = (_fingerprint(hop1, _HOP_FIELDS), _fingerprint(hop2, _HOP_FIELDS), _fingerprint(config, _CFG_FIELDS))
+    hit = _MEMO.get(memo_key)
+    if hit is not None and None not in fp and hit[0] == fp and all(r() is o for r, o in zip(hit[1], (hop1, hop2, config))):
+        return hit[2]
+    plan = _make_plan_uncached(n_prb_grid, n_sym, n_layers, hop1, hop2, config, fill, dev_index)
+    if None not in fp:
+        try:
+            refs = tuple(weakref.ref(o) for o in (hop1, hop2, config))
+        except TypeError:                              # objects that cannot be weakly referenced are not memoised
+            return plan
+        with _PLANS_LOCK:
+            if len(_MEMO) >= _MEMO_MAX:
+                _MEMO.clear()
+            _MEMO[memo_key] = (fp, refs, plan)
+    return plan
+
+
+def _make_plan_uncached(n_prb_grid, n_sym, n_layers, hop1, hop2, config, fill, dev_index) -> Plan:
     desc = _lib.PlanDesc()
     desc.n_prb_grid, desc.n_sym, desc.n_layers = int(n_prb_grid), int(n_sym), int(n_layers)
     smoothing = getattr(config, "Smoothing", None)
@@ -255,11 +301,6 @@ def make_plan(n_prb_grid: int, n_sym: int, n_layers: int, hop1, hop2, config, fi
     for g in range(n_cdm):
         desc.re_mask[g] = int(sum(1 << k for k in range(NRE) if rm1[k, g]))
     desc.hop[0], desc.hop[1] = h1, h2
-    if torch.cuda.is_available():
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-    else:
-        dev_index = -1                                  # host-only plan (CPU-side tests of the planner)
     key = (dev_index, bytes(desc))
     with _PLANS_LOCK:
         plan = _PLANS.get(key)
@@ -309,7 +350,8 @@ def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *,
 
     Returns (channel_est_rg [n_sc, n_sym, L] complex64, noise_est, rsrp, epre, time_alignment
     float64 0-dim, cfo_hz float64 0-dim or an empty (0,) tensor when no hop has two pilot symbols),
-    all on ``received_rg.device`` and without a host synchronisation."""
+    all on ``received_rg.device``.  The call itself never synchronises; the first call with a given
+    (hop1, hop2, config) reads their mask tensors on the host once (see ``make_plan``)."""
     rx = _as_c64(received_rg)
     pil = _as_c64(pilots, device=rx.device)
     if rx.dim() != 2 or pil.dim() != 3:

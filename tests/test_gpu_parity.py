@@ -336,3 +336,69 @@ def test_unit_counts_around_the_resident_cta_count(syms):
     for n in (4, n_sm - 4, n_sm, n_sm + 4, 2 * n_sm - 4, 2 * n_sm, 2 * n_sm + 4):
         out, sc = plan.estimate(data["rx"][:n], data["pilots"][:n // 4], 1.0, 4)
         assert torch.equal(out, full[:n]) and torch.equal(sc, sc_full[:n]), n
+
+
+def test_lazy_conjugate_and_negative_views_are_resolved():
+    """torch keeps ``x.conj()`` as a flag on the same storage: the kernel reads raw storage, so the host layer must
+    materialise such views.  Results must equal the oracle on the conjugated values (as the reference computes)."""
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(4, syms=(3, 10))
+    rx, pil = data["rx"], data["pilots"]
+    rx_c, pil_c = rx.conj(), pil.conj()
+    assert rx_c.is_conj() and rx_c.data_ptr() == rx.data_ptr()
+    out, sc = estimator.srs_channel_estimator_batched(rx_c, pil_c, 1.0, hop1, hop2, cfg, pilot_share=4)
+    want = ce_oracle.estimate(rx[1].conj().resolve_conj().cpu().numpy(), pil[0].conj().resolve_conj().cpu().numpy(), 1.0,
+                              hop1, hop2, cfg)
+    mx, nmse = tol.grid_errors(out[1].cpu().numpy(), want[0])
+    assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (mx, nmse)
+    # a double conjugate and a negated view are the identity / the negated grid
+    ref, _ = estimator.srs_channel_estimator_batched(rx, pil, 1.0, hop1, hop2, cfg, pilot_share=4)
+    twice, _ = estimator.srs_channel_estimator_batched(rx.conj().conj(), pil.conj().conj(), 1.0, hop1, hop2, cfg, pilot_share=4)
+    assert torch.equal(ref, twice)
+    neg = torch.view_as_complex(torch._neg_view(torch.view_as_real(rx)))
+    assert neg.is_neg()
+    out_n, _ = estimator.srs_channel_estimator_batched(neg, pil, 1.0, hop1, hop2, cfg, pilot_share=4)
+    mx, nmse = tol.grid_errors(out_n.cpu().numpy(), (-ref).cpu().numpy())   # (virtual pilots: phase + pi, not bit exact)
+    assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (mx, nmse)
+    one = estimator.srs_channel_estimator(rx_c[1], pil_c[0], 1.0, hop1, hop2, cfg)
+    assert torch.equal(one[0], out[1])
+
+
+def test_caller_supplied_result_buffers_are_validated():
+    """A wrongly shaped / typed / strided ``out`` or ``scalars`` would be overrun by the kernel: every compute call refuses it."""
+    from srsran_ce_pytorch_b200 import estimator
+    hop1, hop2, cfg, data = _config2(8)
+    plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    idx = torch.arange(8, device="cuda", dtype=torch.int64)
+    good_out = torch.empty((8, 3276, 14, 4), dtype=torch.complex64, device="cuda")
+    good_sc = torch.empty((8, 6), dtype=torch.float64, device="cuda")
+    bad_outs = [good_out[:4], torch.empty((8, 3276, 14, 4), dtype=torch.complex128, device="cuda"),
+                torch.empty((8, 3276, 4, 14), dtype=torch.complex64, device="cuda").transpose(2, 3),
+                torch.empty((8, 3276, 14, 4), dtype=torch.complex64)]
+    for bad in bad_outs:
+        with pytest.raises(ValueError):
+            plan.estimate(data["rx"], data["pilots"], 1.0, 4, out=bad)
+        with pytest.raises(ValueError):
+            plan.estimate_indexed(data["rx"], idx, data["pilots"], 1.0, 4, out=bad)
+    for bad in (good_sc[:, :5], good_sc.float(), good_sc.t().contiguous().t()):
+        with pytest.raises(ValueError):
+            plan.estimate(data["rx"], data["pilots"], 1.0, 4, scalars=bad)
+        with pytest.raises(ValueError):
+            plan.estimate_indexed(data["rx"], idx, data["pilots"], 1.0, 4, scalars=bad)
+    a, sa = plan.estimate_indexed(data["rx"], idx, data["pilots"], 1.0, 4, out=good_out, scalars=good_sc, check_index=False)
+    assert a.data_ptr() == good_out.data_ptr() and sa.data_ptr() == good_sc.data_ptr()
+
+
+def test_plan_memo_skips_host_reads_and_sees_in_place_changes():
+    """Repeated drop-in calls with the same HopConfig / EstimatorConfig objects reuse the plan without touching their
+    tensors; an in-place change of a mask tensor (version counter) is noticed."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    hop1 = synth.make_hop(52, 2, 8, [1, 3], "comb4", 2)
+    hop2, cfg = synth.no_hop(), synth.make_config(30e3, "filter", True)
+    hop1.DMRSsymbols = hop1.DMRSsymbols.cuda()
+    hop1.maskPRBs = hop1.maskPRBs.cuda()
+    p1 = estimator.make_plan(52, 14, 4, hop1, hop2, cfg)
+    assert estimator.make_plan(52, 14, 4, hop1, hop2, cfg) is p1
+    hop1.DMRSsymbols[5] = True
+    p2 = estimator.make_plan(52, 14, 4, hop1, hop2, cfg)
+    assert p2 is not p1 and p2.info.n_dmrs_total == 3

@@ -75,11 +75,11 @@ def main():
     ap.add_argument("--units", type=int, default=8192)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="")
-    ap.add_argument("--only", default="", help="substring filter on the point name")
+    ap.add_argument("--only", default="", help="comma-separated substring filters on the point name")
     a = ap.parse_args()
     rows = []
     for p in POINTS:
-        if a.only and a.only not in p[0]:
+        if a.only and not any(o in p[0] for o in a.only.split(",")):
             continue
         r = run(p, a.units, a.reps)
         rows.append(r)
