@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SRSCE_ABI_VERSION 1
+#define SRSCE_ABI_VERSION 2
 
 #define SRSCE_MAX_LAYERS 4
 #define SRSCE_MAX_SYMBOLS 14   /* the reference's CFO tables assume a 14-symbol slot (:809-820) */
@@ -94,6 +94,13 @@ typedef struct srsce_plan_info {
   int32_t fill_terms;         /* operator terms per subcarrier (2 = lerp; CNN operator width otherwise) */
   int32_t has_device;         /* device tables were uploaded */
   int64_t bytes_per_unit;     /* algorithmic HBM bytes of one unit with pilots read once per unit */
+  int32_t fill_tensor;        /* 1: srsce_fill(..., SRSCE_FILL_IMPL_TENSOR) is available for this plan */
+  int32_t fill_tensor_k;      /* pilots per 96-row tile window (K of the banded GEMM before the bf16 term split) */
+  int32_t fill_tensor_terms;  /* bf16 products a_i * x_j accumulated per tile (3 when the operator is exact in bf16) */
+  int32_t fill_tensor_units;  /* units per MMA (N = units * layers in the CDM group * 2) */
+  int32_t fill_tensor_tiles;  /* 96-row tiles of the hop band */
+  int32_t fill_tensor_kinds;  /* distinct operator tiles (first / interior / last ...) kept in shared memory */
+  int32_t fill_tensor_a_terms;/* bf16 terms per operator coefficient (1 when the coefficients are exact in bf16) */
 } srsce_plan_info;
 
 int srsce_abi_version(void);
@@ -109,6 +116,14 @@ int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info);
  *   fill_coef: n_hop_sc * n_cdm * fill_terms float  operator coefficients (linear fill: the row {1-a, a} of the lerp)
  * Pass NULL to skip a table. */
 int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, float* fill_coef);
+
+/* Host-side tables of the tensor-core fill (tests of the host logic; no device needed):
+ *   a_tiles    fill_tensor_kinds * n_cdm * fill_tensor_a_terms blocks of 96 x fill_tensor_k bf16 bit patterns in the
+ *              canonical K-major core-matrix layout [row / 8][k / 8][row % 8][k % 8]
+ *   tile_kind  fill_tensor_tiles int32: operator tile used by each band tile
+ *   tile_k0    fill_tensor_tiles int32: first pilot of each band tile's window
+ * Fails with SRSCE_ERR_UNSUPPORTED (reason in srsce_last_error) when the plan has no tensor-core fill. */
+int srsce_plan_fill_tensor_tables(const srsce_plan* plan, uint16_t* a_tiles, int32_t* tile_kind, int32_t* tile_k0);
 
 /* The fused per-slot path, batched over independent units (one unit = one reference call =
  * one (slot, UE, rx antenna)):
@@ -148,6 +163,21 @@ int srsce_estimate_compact(const srsce_plan* plan, const void* rx_grid, const in
 int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const int64_t rx_strides[3],
                            const int64_t* rx_index, const void* pilots, int32_t pilot_share, double beta,
                            void* ch_est, double* scalars, int64_t n_units, void* stream);
+
+/* The fill operator alone -- the reference's plug-in seam fill_ch_est_cdm_fn of process_hop (:513-517, wired at
+ * :838-841), i.e. ce_rule_tensorized.fill_ch_est_cdm (:237-354) for a SRSCE_FILL_LINEAR plan and
+ * ce_dl_cnn.fill_ch_est_cdm (ce_dl_cnn.py:233-322: the fixed-weight 3-tap "CNN" inpainting) for a SRSCE_FILL_CNN plan,
+ * applied to every CDM group of every hop of a batch of units on a zero grid (what process_hop does at :727):
+ *   h_pilots  complex64 [n_units][n_hops][n_re][n_layers] contiguous: the (smoothed) pilot estimates h_p of each hop
+ *   ch_est    complex64 [n_units][n_sc][n_sym][n_layers], fully overwritten (zero outside band / allocated symbols;
+ *             hop 2 wins where the hops overlap, as in srsce_estimate; no CFO rotation -- that is not part of the fill)
+ *   impl      SRSCE_FILL_IMPL_DIRECT: operator rows applied with float32 FMAs by the fused kernel's writer warps;
+ *             SRSCE_FILL_IMPL_TENSOR: the same operator as a banded GEMM on the tcgen05 tensor cores (bf16 operand
+ *             terms, float32 accumulation in tensor memory).  Available for single-hop plans on a 14-symbol grid
+ *             whose operator tiles fit in shared memory; SRSCE_ERR_UNSUPPORTED otherwise (srsce_plan_info.fill_tensor).
+ * Both implementations are HBM-write bound (0.4 FLOP/B); see DESIGN.md section 3.1. */
+enum { SRSCE_FILL_IMPL_DIRECT = 0, SRSCE_FILL_IMPL_TENSOR = 1 };
+int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64_t n_units, int32_t impl, void* stream);
 
 /* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
 int srsce_last_launch_count(void);

@@ -13,10 +13,11 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SRSCE_LIBRARY", _HERE / "libsrsce.so"))   # override: A/B runs of two builds
 
 MAX_SYMBOLS = 14
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SMOOTH = {"none": 0, "mean": 1, "filter": 2}
 FILL_LINEAR, FILL_CNN = 0, 1
+FILL_IMPL = {"direct": 0, "tensor": 1}
 
 ERR_INVALID, ERR_ASSERT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA = -1, -2, -3, -4, -5
 
@@ -38,7 +39,9 @@ class PlanInfo(C.Structure):
                 ("n_re", C.c_int32), ("n_dmrs_total", C.c_int32), ("n_taps", C.c_int32),
                 ("n_virtual", C.c_int32), ("fft_size", C.c_int32), ("cfo_defined", C.c_int32),
                 ("smem_bytes", C.c_int32), ("threads", C.c_int32), ("fill_terms", C.c_int32),
-                ("has_device", C.c_int32), ("bytes_per_unit", C.c_int64)]
+                ("has_device", C.c_int32), ("bytes_per_unit", C.c_int64), ("fill_tensor", C.c_int32),
+                ("fill_tensor_k", C.c_int32), ("fill_tensor_terms", C.c_int32), ("fill_tensor_units", C.c_int32),
+                ("fill_tensor_tiles", C.c_int32), ("fill_tensor_kinds", C.c_int32), ("fill_tensor_a_terms", C.c_int32)]
 
 
 def _load() -> C.CDLL:
@@ -66,6 +69,10 @@ def _load() -> C.CDLL:
     lib.srsce_estimate_indexed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.srsce_estimate_indexed.restype = C.c_int
+    lib.srsce_plan_fill_tensor_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.srsce_plan_fill_tensor_tables.restype = C.c_int
+    lib.srsce_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.srsce_fill.restype = C.c_int
     lib.srsce_last_launch_count.restype = C.c_int
     if lib.srsce_abi_version() != ABI_VERSION:
         raise ImportError(f"libsrsce.so ABI {lib.srsce_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
@@ -75,7 +82,7 @@ def _load() -> C.CDLL:
 lib = _load()
 
 EXPORTS = ("srsce_abi_version", "srsce_last_error", "srsce_plan_create", "srsce_plan_destroy", "srsce_plan_query",
-           "srsce_plan_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed",
+           "srsce_plan_tables", "srsce_plan_fill_tensor_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed", "srsce_fill",
            "srsce_last_launch_count")
 
 

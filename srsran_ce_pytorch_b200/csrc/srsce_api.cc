@@ -73,6 +73,13 @@ int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info) {
   info->fill_terms = plan->impl.fill_terms_host;
   info->has_device = plan->impl.device >= 0;
   info->bytes_per_unit = plan->impl.bytes_per_unit;
+  info->fill_tensor = plan->impl.has_fill_tc ? 1 : 0;
+  info->fill_tensor_k = plan->impl.fill_tc.k_tile;
+  info->fill_tensor_terms = plan->impl.fill_tc.n_prod;
+  info->fill_tensor_units = plan->impl.fill_tc.units;
+  info->fill_tensor_tiles = plan->impl.fill_tc.n_tiles;
+  info->fill_tensor_kinds = plan->impl.fill_tc.n_kinds;
+  info->fill_tensor_a_terms = plan->impl.fill_tc.n_a;
   return SRSCE_OK;
 }
 
@@ -82,6 +89,18 @@ int srsce_plan_tables(const srsce_plan* plan, double* taps, int32_t* fill_idx, f
   if (taps) memcpy(taps, p.taps.data(), p.taps.size() * sizeof(double));
   if (fill_idx) memcpy(fill_idx, p.fill_idx.data(), p.fill_idx.size() * sizeof(int32_t));
   if (fill_coef) memcpy(fill_coef, p.fill_coef.data(), p.fill_coef.size() * sizeof(float));
+  return SRSCE_OK;
+}
+
+int srsce_plan_fill_tensor_tables(const srsce_plan* plan, uint16_t* a_tiles, int32_t* tile_kind, int32_t* tile_k0) {
+  if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
+  const srsce::Plan& p = plan->impl;
+  if (!p.has_fill_tc) return fail(SRSCE_ERR_UNSUPPORTED, "tensor-core fill unavailable for this plan: " + p.fill_tc_why);
+  if (a_tiles) memcpy(a_tiles, p.fill_tc_a.data(), p.fill_tc_a.size() * sizeof(uint16_t));
+  for (int m = 0; m < p.fill_tc.n_tiles; ++m) {
+    if (tile_kind) tile_kind[m] = p.fill_tc.tile_kind[m];
+    if (tile_k0) tile_k0[m] = p.fill_tc.tile_k0[m];
+  }
   return SRSCE_OK;
 }
 
@@ -149,6 +168,25 @@ int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const i
     std::string err;
     const int rc = srsce::launch_estimate(plan->impl, rx_grids, rx_strides, pilots, pilot_share, beta, ch_est, scalars,
                                           n_units, stream, &g_launches, err, nullptr, nullptr, rx_index);
+    return rc == SRSCE_OK ? rc : fail(rc, err);
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
+int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64_t n_units, int32_t impl, void* stream) {
+  g_launches = 0;
+  if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
+  if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
+  if (n_units > 0 && (!h_pilots || !ch_est)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if (impl != SRSCE_FILL_IMPL_DIRECT && impl != SRSCE_FILL_IMPL_TENSOR) return fail(SRSCE_ERR_INVALID, "unknown fill implementation");
+  if ((reinterpret_cast<uintptr_t>(ch_est) & 15u) || (reinterpret_cast<uintptr_t>(h_pilots) & 7u))
+    return fail(SRSCE_ERR_INVALID, "buffers must be aligned (ch_est 16 B, h_pilots 8 B)");
+  try {
+    std::string err;
+    const int rc = impl == SRSCE_FILL_IMPL_TENSOR
+                       ? srsce::launch_fill_tc(plan->impl, h_pilots, ch_est, n_units, stream, &g_launches, err)
+                       : srsce::launch_fill_direct(plan->impl, h_pilots, ch_est, n_units, stream, &g_launches, err);
     return rc == SRSCE_OK ? rc : fail(rc, err);
   } catch (const std::exception& e) {
     return fail(SRSCE_ERR_INVALID, e.what());

@@ -99,6 +99,38 @@ struct PlanDev {
   const float* fill_coef;                 // [n_cdm][band rows][fill_terms]
 };
 
+// ---- tensor-core fill (srsce_fill_tc.cu): the band interpolation operator of fill_ch_est_cdm as a banded GEMM
+//      D[96 band rows x (unit, layer, re/im)] = A_tile[96 x K] * X[K x (unit, layer, re/im)]   per CDM group,
+// bf16 operands (float32 values split into bf16 terms, so the float32 result is reproduced), float32 accumulators
+// in tensor memory.  A tile = 8 PRBs: interior tiles share one operator block because the rows repeat per PRB.
+constexpr int kFillTileRows = 96;
+constexpr int kFillMaxTiles = 48;      // ceil(4096 / 96) + slack
+constexpr int kFillMaxKinds = 6;       // distinct operator tiles kept in shared memory (first / interior / last ...)
+constexpr int kFillEpiWarps = 8;       // two warpgroups; the warps of lane quadrant 3 (rows 96..127 of the MMA) idle
+constexpr int kFillLoadWarps = 4;
+constexpr int kFillThreads = 32 * (kFillEpiWarps + kFillLoadWarps + 1);
+struct FillTcDev {
+  int32_t n_sc, n_layers, n_cdm, n_re;
+  int32_t band_sc0, band_rows, n_tiles;
+  int32_t sym0, sym1;                  // allocated symbols [sym0, sym1)
+  int32_t k_tile;                      // pilots per tile window (multiple of 16)
+  int32_t units;                       // units per work item (UMMA N = units * layers in group * 2)
+  int32_t n_a;                         // bf16 terms of the operator coefficients (1 when they are exact in bf16)
+  int32_t n_kinds;
+  int32_t n_prod;                      // bf16 products a_i * x_j kept (i + j <= 2)
+  int32_t prod_a[6], prod_x[6];
+  int32_t n_cols[2];                   // UMMA N of each CDM group
+  int32_t col0[2];                     // first tensor-memory column of each group inside an accumulator stage
+  int32_t a_block_bytes;               // one (kind, group, term) operator block: 96 x k_tile bf16, canonical K-major
+  int32_t b_block_bytes[2];            // one (group, term) block of X: n_cols[g] x k_tile bf16
+  int32_t b_group_off[2];              // byte offset of group g inside a B stage
+  int32_t b_stage_bytes;
+  int32_t off_a, off_b, off_tile, off_bar, smem_bytes;
+  uint8_t tile_kind[kFillMaxTiles];
+  int32_t tile_k0[kFillMaxTiles];      // first pilot of each tile's window
+  const uint16_t* a_tiles;             // device copy: [kind][group][term] blocks
+};
+
 struct Plan {
   srsce_plan_desc desc;
   PlanDev dev;                        // layout for the reference call shape (dense output, one received grid per unit)
@@ -117,6 +149,12 @@ struct Plan {
   void* d_fill_idx = nullptr;
   void* d_fill_coef = nullptr;
   int64_t bytes_per_unit = 0;
+  // tensor-core fill
+  bool has_fill_tc = false;
+  std::string fill_tc_why;            // why the tensor-core fill is unavailable for this plan
+  FillTcDev fill_tc;
+  std::vector<uint16_t> fill_tc_a;    // host copy of the operator blocks (bf16 bit patterns)
+  void* d_fill_tc_a = nullptr;
 };
 
 // srsce_plan.cc
@@ -131,5 +169,12 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
                     void* stream, int* launches, std::string& err, void* out_compact = nullptr,
                     void* rot_compact = nullptr, const int64_t* rx_index = nullptr);
 int max_dynamic_smem();
+int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
+                       std::string& err);
+
+// srsce_fill_tc.cu
+int prepare_fill_tc(Plan& p, std::string& err);
+int launch_fill_tc(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
+                   std::string& err);
 
 }  // namespace srsce

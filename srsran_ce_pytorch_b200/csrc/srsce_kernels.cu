@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "srsce_internal.h"
+#include "srsce_device.cuh"
 
 namespace srsce {
 
@@ -92,16 +93,6 @@ __device__ long long* g_prof_buf = nullptr;       // [gridDim.x][kProfSlots] cyc
 #define PROF_MARK(cond, k) do { } while (0)
 #define PROF_FLUSH(cond, base) do { } while (0)
 #endif
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 
 // Named barriers: 0 is __syncthreads (whole CTA); 1 joins the estimator warps only; 2 ("full") hands
 // hall[b] + store-slot table b from the estimator warps to the writer warps, 4+b ("empty") hands them back.
@@ -246,45 +237,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Writer hot loop for a full 32-row tile of a 14-symbol grid with LL (2 or 4) layers: every lane owns one 16-byte
-// store slot (symbol, layer pair) and walks the rows with compile-time strides, so each row costs one LDS.128 and
-// one STG.128 with the offsets folded into the instructions.  (32 / cols) rows are covered per warp pass.
-template <int LL, bool ROT>
-__device__ __forceinline__ void stream_full_tile(const float4* __restrict__ src, float4* __restrict__ dst, bool on,
-                                                 float2 rot0, float2 rot1) {
-  constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = (kTileRows + kRowsPerPass - 1) / kRowsPerPass;
-  static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
-#pragma unroll
-  for (int p = 0; p < kPasses; ++p) {
-    float4 v = on ? src[p * (kRowsPerPass * LL / 2)] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ROT) {
-      const float2 a = cmul(make_float2(v.x, v.y), rot0), b = cmul(make_float2(v.z, v.w), rot1);
-      v = make_float4(a.x, a.y, b.x, b.y);
-    }
-    __stcs(dst + p * (kRowsPerPass * kCols), v);
-  }
-}
-
-// Odd layer counts (1 or 3): the two complex64 elements of a 16-byte slot belong to different (symbol, layer)
-// pairs, so each is fetched (8 bytes) and gated on its own; strides are still compile-time constants.
-template <int LL, bool ROT>
-__device__ __forceinline__ void stream_full_tile_odd(const float2* __restrict__ src0, const float2* __restrict__ src1,
-                                                     float4* __restrict__ dst, bool on0, bool on1, float2 rot0,
-                                                     float2 rot1) {
-  constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = kTileRows / kRowsPerPass;
-  static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
-#pragma unroll
-  for (int p = 0; p < kPasses; ++p) {
-    float2 a = on0 ? src0[p * (kRowsPerPass * LL)] : make_float2(0.f, 0.f);
-    float2 b = on1 ? src1[p * (kRowsPerPass * LL)] : make_float2(0.f, 0.f);
-    if (ROT) {
-      a = cmul(a, rot0);
-      b = cmul(b, rot1);
-    }
-    __stcs(dst + p * (kRowsPerPass * kCols), make_float4(a.x, a.y, b.x, b.y));
-  }
-}
-
 // The same for two hops: rows inside hop 2's band take hop 2's value on the symbols of hop 2's allocation
 // (it wins where the hops overlap), otherwise hop 1's on hop 1's allocated symbols, otherwise zero.
 template <int LL, bool ROT>
@@ -324,7 +276,8 @@ __global__ void __launch_bounds__(cta_threads(NA, TWO_HOPS), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg_arg,
-                float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index) {
+                float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index,
+                const float2* __restrict__ h_in) {
 #ifdef SRSCE_PROFILING
   const int dbg = dbg_arg;                                  // ablation bits (profiling build only)
 #else
@@ -369,7 +322,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   PROF_DECL
   // gather the pilot REs of unit `un` into a stage buffer (8-byte async copies; nothing waits here)
   auto stage_unit = [&](long long un, float2* dst) {
-    if (!STAGED || un >= n_units || (dbg & 4)) return;          // (unstaged fallback / ablation bit 2: no staging traffic)
+    if (!STAGED || un >= n_units || (dbg & 4) || h_in != nullptr) return;   // (unstaged fallback / ablation bit 2 / fill-only launch)
     const float2* rxn = rx + (rx_index ? __ldg(rx_index + un) : un) * su;     // several units may share one received grid
     for (int hh = 0; hh < n_hops; ++hh) {
       const HopDev& H = P.hop[hh];
@@ -419,6 +372,22 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 
   int it = 0;
   for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+    if (h_in != nullptr) {
+      // fill-only launch (srsce_fill, direct implementation): the smoothed pilots [hop][N][L] of the unit are an
+      // input; transpose them into hall ([hop][layer][N]) and hand them to the writer warps -- phase B alone, i.e.
+      // fill_ch_est_cdm (:237-354 / ce_dl_cnn.py:233-322) for every CDM group of every hop
+      const int hb = (P.hall_bufs == 2) ? (it & 1) : 0;
+      float2* const hdst = hall0 + hb * (n_hops * L * N);
+      if (it >= P.hall_bufs) bar_sync(kBarEmpty + hb, kCtaThreads);
+      const float2* __restrict__ hu = h_in + u * ((long long)n_hops * N * L);
+      for (int idx = tid; idx < n_hops * N * L; idx += kThreads) {
+        const int hh = idx / (N * L), rem = idx - hh * (N * L), i = rem / L, l = rem - i * L;
+        hdst[hh * L * N + l * N + i] = __ldg(hu + idx);
+      }
+      build_store_table(m.col[hb]);
+      bar_arrive(kBarFull + hb, kCtaThreads);
+      continue;
+    }
     const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
@@ -761,7 +730,9 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           }
           sync_a<NA>();
+          PROF_MARK(tid == 0, 13);
           fft_dif_inverse<NA>(ext, nl, M, log2M, P.twiddle);
+          PROF_MARK(tid == 0, 14);
           for (int t = tid; t < 2 * SRSCE_TA_WINDOW; t += kThreads) {
             const int bin = (t < SRSCE_TA_WINDOW) ? t : SRSCE_TA_FFT - 2 * SRSCE_TA_WINDOW + t;
             const int pos = dif_position(bin & (M - 1), M);
@@ -773,6 +744,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           }
           sync_a<NA>();
+          PROF_MARK(tid == 0, 15);
         }
         if (warp < n_hops) {
           // first maximum of each window; ties keep the lower index, as torch.max / np.argmax
@@ -1013,7 +985,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 }
 
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
-                         double, float2*, double*, long long, int, float2*, float2*, const long long*);
+                         double, float2*, double*, long long, int, float2*, float2*, const long long*, const float2*);
 
 template <int NA, bool STAGED>
 KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
@@ -1025,8 +997,8 @@ KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
   return has_rot ? estimate_kernel<NA, 1, false, true, STAGED> : estimate_kernel<NA, 1, false, false, STAGED>;
 }
 
-KernelFn pick_kernel(const PlanDev& v) {
-  const bool rot = v.cfo_compensate && v.cfo_defined, two = v.n_hops == 2;
+KernelFn pick_kernel(const PlanDev& v, bool fill_only = false) {
+  const bool rot = v.cfo_compensate && v.cfo_defined && !fill_only, two = v.n_hops == 2;   // (the fill has no CFO rotation)
   if (v.y_bufs == 0) return pick_kernel_na<512, false>(v.vec, two, rot);    // the planner pairs the unstaged layout with NA = 512
   return v.est_threads == 512 ? pick_kernel_na<512, true>(v.vec, two, rot) : pick_kernel_na<256, true>(v.vec, two, rot);
 }
@@ -1107,6 +1079,11 @@ int upload_plan(Plan& p, std::string& err) {
     return SRSCE_ERR_CUDA;
   }
   auto prepare = [&](const PlanDev& v, int* per_sm) -> int {
+    KernelFn fill_fn = pick_kernel(v, true);            // srsce_fill (direct) launches the variant without the final rotation
+    if ((e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fill_fn), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem())) != cudaSuccess) {
+      err = cuda_msg("cudaFuncSetAttribute(smem)", e);
+      return SRSCE_ERR_CUDA;
+    }
     KernelFn fn = pick_kernel(v);
     // the limit is per kernel variant, not per plan: always raise it to the architectural maximum so that
     // plans with different footprints can share a variant
@@ -1130,14 +1107,15 @@ int upload_plan(Plan& p, std::string& err) {
   }
   p.n_sms = sms;
   p.device = dev;
-  return SRSCE_OK;
+  return prepare_fill_tc(p, err);
 }
 
 void release_plan(Plan& p) {
   if (p.d_twiddle) cudaFree(p.d_twiddle);
   if (p.d_fill_idx) cudaFree(p.d_fill_idx);
   if (p.d_fill_coef) cudaFree(p.d_fill_coef);
-  p.d_twiddle = p.d_fill_idx = p.d_fill_coef = nullptr;
+  if (p.d_fill_tc_a) cudaFree(p.d_fill_tc_a);
+  p.d_twiddle = p.d_fill_idx = p.d_fill_coef = p.d_fill_tc_a = nullptr;
 }
 
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots, int pilot_share,
@@ -1161,9 +1139,32 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
       v, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
       debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact),
-      reinterpret_cast<const long long*>(rx_index));
+      reinterpret_cast<const long long*>(rx_index), nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { err = cuda_msg("kernel launch", e); return SRSCE_ERR_CUDA; }
+  *launches = 1;
+  return SRSCE_OK;
+}
+
+// srsce_fill, direct implementation: the fused kernel's writer warps fed with given smoothed pilots (no phase A).
+int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
+                       std::string& err) {
+  *launches = 0;
+  if (p.device < 0) { err = "plan has no CUDA device (created without a GPU); there is no CPU compute path"; return SRSCE_ERR_NO_DEVICE; }
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (dev != p.device) { err = "plan was created on another CUDA device"; return SRSCE_ERR_INVALID; }
+  if (n_units == 0) return SRSCE_OK;
+  const bool pair = p.has_pair;                       // no gather, light estimator side: the CTA pair when the plan has one
+  const PlanDev& v = pair ? p.dev_pair : p.dev;
+  KernelFn fn = pick_kernel(v, true);
+  const long long cap = (long long)p.n_sms * (pair ? p.ctas_per_sm_pair : p.ctas_per_sm);
+  const unsigned grid = unsigned(n_units < cap ? n_units : cap);
+  fn<<<grid, cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
+      v, nullptr, 0, 0, 0, nullptr, 1, 1.0, static_cast<float2*>(out), nullptr, (long long)n_units, 0, nullptr, nullptr,
+      nullptr, static_cast<const float2*>(h_pilots));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { err = cuda_msg("fill launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;
   return SRSCE_OK;
 }

@@ -191,6 +191,153 @@ static void emit_rows(const std::vector<SparseRow>& rows, int n_known, int terms
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core fill: pack the operator rows (lerp or CNN inpainting) into bf16 tiles for tcgen05.mma.
+// ---------------------------------------------------------------------------------------------
+static uint16_t bf16_rn(float f) {                      // round to nearest even, finite inputs only
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return uint16_t(u >> 16);
+}
+static float bf16_to_float(uint16_t h) {
+  const uint32_t u = uint32_t(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Fills p.fill_tc / p.fill_tc_a from the packed operator rows (p.fill_idx / p.fill_coef, fill_terms_host terms per
+// row).  Unsupported geometries leave has_fill_tc = false with the reason in fill_tc_why; the direct fill remains.
+static void build_fill_tc(Plan& p, int n_hops) {
+  const srsce_plan_desc& d = p.desc;
+  FillTcDev& f = p.fill_tc;
+  memset(&f, 0, sizeof f);
+  p.has_fill_tc = false;
+  p.fill_tc_a.clear();
+  auto no = [&](const char* why) { p.fill_tc_why = why; };
+  if (n_hops != 1) return no("two hops");
+  if (d.n_sym != SRSCE_MAX_SYMBOLS) return no("grid is not 14 symbols");
+  const int L = d.n_layers, G = (L + 1) / 2, T = p.fill_terms_host, N = p.dev.n_re, rows = p.band_rows;
+  const int n_tiles = (rows + kFillTileRows - 1) / kFillTileRows;
+  if (n_tiles > kFillMaxTiles) return no("too many tiles");
+  // pilot window of every tile
+  std::vector<int> k0(n_tiles), k1(n_tiles);
+  int span = 1;
+  for (int m = 0; m < n_tiles; ++m) {
+    int lo = 1 << 30, hi = -1;
+    for (int g = 0; g < G; ++g)
+      for (int r = m * kFillTileRows; r < std::min(rows, (m + 1) * kFillTileRows); ++r)
+        for (int t = 0; t < T; ++t)
+          if (p.fill_coef[(size_t(g) * rows + r) * T + t] != 0.f) {
+            lo = std::min(lo, p.fill_idx[size_t(g) * rows + r] + t);
+            hi = std::max(hi, p.fill_idx[size_t(g) * rows + r] + t);
+          }
+    if (hi < 0) lo = hi = 0;
+    k0[m] = lo;
+    k1[m] = hi;
+    span = std::max(span, hi - lo + 1);
+  }
+  const int kt = ((span + 15) / 16) * 16;
+  if (kt > 128) return no("operator window wider than 128 pilots per tile");
+  // dense float tiles [m][g][96][kt], then their bf16 terms
+  auto tile_of = [&](int m, int g, std::vector<float>& a) {
+    a.assign(size_t(kFillTileRows) * kt, 0.f);
+    for (int r = m * kFillTileRows; r < std::min(rows, (m + 1) * kFillTileRows); ++r)
+      for (int t = 0; t < T; ++t) {
+        const float c = p.fill_coef[(size_t(g) * rows + r) * T + t];
+        if (c != 0.f) a[size_t(r - m * kFillTileRows) * kt + (p.fill_idx[size_t(g) * rows + r] + t - k0[m])] = c;
+      }
+  };
+  std::vector<std::vector<float>> kinds;              // [kind] = concatenation over groups
+  std::vector<float> a, cat;
+  for (int m = 0; m < n_tiles; ++m) {
+    cat.clear();
+    for (int g = 0; g < G; ++g) {
+      tile_of(m, g, a);
+      cat.insert(cat.end(), a.begin(), a.end());
+    }
+    int kind = -1;
+    for (size_t q = 0; q < kinds.size() && kind < 0; ++q)
+      if (kinds[q] == cat) kind = int(q);
+    if (kind < 0) {
+      if (int(kinds.size()) == kFillMaxKinds) return no("operator tiles do not repeat (more than 6 distinct tiles)");
+      kind = int(kinds.size());
+      kinds.push_back(cat);
+    }
+    f.tile_kind[m] = uint8_t(kind);
+    f.tile_k0[m] = k0[m];
+  }
+  // bf16 terms: a = a0 + a1 + a2 (each the bf16 rounding of what is left); keep as many as are non-zero anywhere
+  int n_a = 1;
+  for (const auto& kd : kinds)
+    for (float v : kd) {
+      const float r1 = v - bf16_to_float(bf16_rn(v));
+      if (r1 != 0.f) {
+        n_a = std::max(n_a, 2);
+        if (r1 - bf16_to_float(bf16_rn(r1)) != 0.f) n_a = 3;
+      }
+    }
+  f.n_a = n_a;
+  f.n_prod = 0;
+  for (int i = 0; i < n_a; ++i)
+    for (int j = 0; i + j <= 2; ++j) {
+      f.prod_a[f.n_prod] = i;
+      f.prod_x[f.n_prod] = j;
+      ++f.n_prod;
+    }
+  f.k_tile = kt;
+  f.units = kt <= 32 ? 32 : (kt <= 64 ? 16 : 8);
+  f.n_kinds = int(kinds.size());
+  f.a_block_bytes = kFillTileRows * kt * 2;
+  p.fill_tc_a.assign(size_t(f.n_kinds) * G * n_a * kFillTileRows * kt, 0);
+  for (int q = 0; q < f.n_kinds; ++q)
+    for (int g = 0; g < G; ++g)
+      for (int r = 0; r < kFillTileRows; ++r)
+        for (int k = 0; k < kt; ++k) {
+          float v = kinds[q][(size_t(g) * kFillTileRows + r) * kt + k];
+          for (int i = 0; i < n_a; ++i) {
+            const uint16_t h = bf16_rn(v);
+            v -= bf16_to_float(h);
+            // canonical K-major core-matrix layout: [row / 8][k / 8][row % 8][k % 8]
+            const size_t blk = (size_t(q) * G + g) * n_a + i;
+            p.fill_tc_a[blk * kFillTileRows * kt + (size_t(r >> 3) * (kt >> 3) + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7)] = h;
+          }
+        }
+  f.n_sc = p.dev.n_sc;
+  f.n_layers = L;
+  f.n_cdm = G;
+  f.n_re = N;
+  f.band_sc0 = p.dev.hop[0].band_sc0;
+  f.band_rows = rows;
+  f.n_tiles = n_tiles;
+  f.sym0 = p.dev.hop[0].start_symbol;
+  f.sym1 = p.dev.hop[0].end_symbol;
+  int col = 0, boff = 0;
+  for (int g = 0; g < G; ++g) {
+    const int nl = std::min(2, L - 2 * g);
+    f.n_cols[g] = f.units * nl * 2;
+    f.col0[g] = col;
+    col += f.n_cols[g];
+    f.b_block_bytes[g] = f.n_cols[g] * kt * 2;
+    f.b_group_off[g] = boff;
+    boff += 3 * f.b_block_bytes[g];
+  }
+  f.b_stage_bytes = boff;
+  auto up128 = [](int b) { return (b + 127) / 128 * 128; };
+  f.off_a = 0;
+  f.off_b = up128(f.n_kinds * G * n_a * f.a_block_bytes);
+  f.off_tile = f.off_b + up128(2 * f.b_stage_bytes);
+  f.off_bar = f.off_tile + kFillEpiWarps * kTileRows * SRSCE_MAX_LAYERS * 8;
+  f.smem_bytes = f.off_bar + 128;
+  // (the MMA reads 128 operator rows where a block holds 96: the 32 phantom rows of the last block fall into the X
+  //  stages behind it, 64 * k_tile bytes at most, always inside the allocation)
+  if (f.smem_bytes > 227 * 1024) return no("operator tiles + staging exceed 227 KB of shared memory");
+  if (col > 256) return no("accumulators exceed half of tensor memory");
+  p.has_fill_tc = true;
+  p.fill_tc_why.clear();
+}
+
 #define FAIL(code, ...)                                  \
   do {                                                   \
     char buf_[256];                                      \
@@ -518,6 +665,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       FAIL(SRSCE_ERR_UNSUPPORTED, "geometry needs %d bytes of shared memory per unit (limit %d)", v.smem_bytes, 227 * 1024);
   }
 
+  build_fill_tc(p, n_hops);
   p.bytes_per_unit = 8LL * (int64_t(G) * N * s_total + int64_t(N) * s_total * L + int64_t(v.n_sc) * d.n_sym * L) + 48;
   return SRSCE_OK;
 }

@@ -89,6 +89,17 @@ class Plan:
         _lib.raise_for(lib.srsce_plan_tables(self._h, taps.ctypes.data, idx.ctypes.data, coef.ctypes.data))
         return taps[:i.n_taps], idx, coef
 
+    def fill_tensor_tables(self):
+        """Operator tiles of the tensor-core fill as float64 [kinds, n_cdm, 96, K] (bf16 terms summed), the tile -> kind
+        map and the first pilot of every tile's window."""
+        i = self.info
+        a = np.zeros((i.fill_tensor_kinds, i.n_cdm, i.fill_tensor_a_terms, 12, i.fill_tensor_k // 8, 8, 8), dtype=np.uint16)
+        kind = np.zeros(i.fill_tensor_tiles, dtype=np.int32)
+        k0 = np.zeros(i.fill_tensor_tiles, dtype=np.int32)
+        _lib.raise_for(lib.srsce_plan_fill_tensor_tables(self._h, a.ctypes.data, kind.ctypes.data, k0.ctypes.data))
+        f = (a.astype(np.uint32) << 16).view(np.float32).astype(np.float64).sum(axis=2)    # [kind, g, row/8, k/8, row%8, k%8]
+        return f.transpose(0, 1, 2, 4, 3, 5).reshape(i.fill_tensor_kinds, i.n_cdm, 96, i.fill_tensor_k), kind, k0
+
     # ---- argument checks shared by the compute calls
     @staticmethod
     def _materialize(t: torch.Tensor) -> torch.Tensor:
@@ -188,6 +199,34 @@ class Plan:
                                                       int(pilot_share), float(beta), ch.data_ptr(), rot.data_ptr(),
                                                       scalars.data_ptr(), n_units, C.c_void_p(stream)))
         return ch, rot, scalars
+
+    def fill(self, h_pilots: torch.Tensor, impl: str = "direct", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The fill operator alone (``srsce_fill``): h_pilots [B, n_hops, n_re, L] complex64 (the smoothed pilot
+        estimates of each hop) -> dense [B, n_sc, n_sym, L] grid, zero outside the band / allocated symbols.
+        ``impl`` = "direct" (float32 FMAs in the fused kernel's writer warps) or "tensor" (tcgen05 banded GEMM;
+        raises NotImplementedError when ``info.fill_tensor`` is 0)."""
+        i = self.info
+        n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
+        if not h_pilots.is_cuda:
+            raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
+        if h_pilots.dtype != torch.complex64:
+            raise TypeError("h_pilots must be complex64")
+        if h_pilots.dim() != 4 or tuple(h_pilots.shape[1:]) != (n_hops, i.n_re, i.n_layers):
+            raise IndexError(f"h_pilots shape {tuple(h_pilots.shape)} != [B, {n_hops}, {i.n_re}, {i.n_layers}]")
+        if impl not in _lib.FILL_IMPL:
+            raise ValueError(f"unknown fill implementation {impl!r}")
+        h_pilots = self._materialize(h_pilots).contiguous()
+        n_units = int(h_pilots.shape[0])
+        if out is None:
+            out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=h_pilots.device)
+        elif tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers) or not out.is_contiguous() \
+                or out.dtype != torch.complex64 or out.device != h_pilots.device or out.is_conj() or out.is_neg():
+            raise ValueError("out must be a contiguous complex64 [B, n_sc, n_sym, L] tensor on h_pilots.device")
+        with torch.cuda.device(h_pilots.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.raise_for(lib.srsce_fill(self._h, h_pilots.data_ptr(), out.data_ptr(), n_units, _lib.FILL_IMPL[impl],
+                                          C.c_void_p(stream)))
+        return out
 
     def expand_compact(self, ch: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
         """[B, n_hops, n_sc, L] x [B, n_sym] -> the dense [B, n_sc, n_sym, L] grid of the reference contract
@@ -367,3 +406,45 @@ def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *,
 
 def unpack_scalars(scalars: torch.Tensor) -> dict:
     return {name: scalars[:, k] for k, name in enumerate(_SCALAR_FIELDS)}
+
+
+def fill_ch_est_cdm(channel_in: torch.Tensor, estimated: torch.Tensor, hop, i_cdm: int, *, fill: str = "linear",
+                    impl: str = "direct") -> torch.Tensor:
+    """Drop-in for the reference's ``fill_ch_est_cdm(channel_in, estimated, hop, i_cdm)`` -- the plug-in seam
+    ``fill_ch_est_cdm_fn`` of process_hop (ce_rule_tensorized.py:237-354 for ``fill="linear"``,
+    ce_dl_cnn.py:233-322 for ``fill="cnn"``): returns a copy of ``channel_in`` [n_sc, n_sym, L] whose band rows /
+    allocated symbols hold, for the layers of CDM group ``i_cdm`` (1-based, as in the reference), the pilots
+    ``estimated`` [n_re, layers in the group] interpolated over the hop band.  The interpolation and the
+    replication over the symbols run in ``srsce_fill``; the copy into ``channel_in`` is a torch slice assignment."""
+    ch = torch.as_tensor(channel_in)
+    if not ch.is_cuda:
+        raise RuntimeError("srsran_ce_pytorch_b200 computes on CUDA tensors only (no CPU fallback)")
+    if not torch.is_complex(ch):
+        ch = ch.to(torch.complex64)
+    est = _as_c64(estimated, device=ch.device)
+    if ch.dim() != 3 or est.dim() != 2:
+        raise IndexError("expected channel_in [n_sc, n_sym, L] and estimated [n_re, layers in the CDM group]")
+    n_sc, n_sym, n_lg = ch.shape[0], ch.shape[1], est.shape[1]
+    rm = _host(hop.DMRSREmask).astype(bool)
+    if rm.ndim == 1:
+        rm = rm.reshape(NRE, -1)
+    col = rm[:, int(i_cdm) - 1]
+    if not col.any() or int(hop.nPRBs) == 0:
+        return ch.clone()                                               # ce_dl_cnn.py:289-291
+    sub = type("Hop", (), {})()
+    sub.DMRSsymbols, sub.maskPRBs = hop.DMRSsymbols, hop.maskPRBs
+    sub.DMRSREmask = torch.as_tensor(col).reshape(NRE, 1)
+    sub.PRBstart, sub.nPRBs = hop.PRBstart, hop.nPRBs
+    sub.startSymbol, sub.nAllocatedSymbols = hop.startSymbol, hop.nAllocatedSymbols
+    none = type("Hop", (), {})()
+    none.DMRSsymbols = torch.zeros((0,), dtype=torch.bool)
+    cfg = type("Cfg", (), {})()
+    cfg.scs, cfg.CyclicPrefixDurations, cfg.Smoothing, cfg.CFOCompensate = 30e3, torch.zeros(14, dtype=torch.float64), "none", False
+    plan = make_plan(n_sc // NRE, n_sym, n_lg, sub, none, cfg, fill, device=ch.device)
+    grid = plan.fill(est.reshape(1, 1, est.shape[0], n_lg), impl=impl)[0]
+    out = ch.clone()
+    sc0, sc1 = NRE * int(hop.PRBstart), NRE * (int(hop.PRBstart) + int(hop.nPRBs))
+    t0, t1 = int(hop.startSymbol), int(hop.startSymbol) + int(hop.nAllocatedSymbols)
+    l0 = (int(i_cdm) - 1) * 2
+    out[sc0:sc1, t0:t1, l0:l0 + n_lg] = grid[sc0:sc1, t0:t1, :].to(out.dtype)
+    return out

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.srsce_abi_version() == 1
+    assert _lib.lib.srsce_abi_version() == _lib.ABI_VERSION == 2
 
 
 def _plan(pattern, n_prbs, n_layers, smoothing="filter", fill="linear", grid=52, syms=(2, 11), start=3, **kw):
@@ -151,3 +151,41 @@ def test_fill_operator_property_random_masks(bits0, n_prbs, shift, fill):
         for t in range(coef.shape[2]):
             got += coef[g, :, t, None].astype(np.float64) * h[np.minimum(idx[g] + t, n - 1)].astype(np.complex128)
         assert np.abs(got - want).max() <= 3e-6 * max(np.abs(want).max(), 1e-30)
+
+
+@pytest.mark.parametrize("fill", ["linear", "cnn"])
+@pytest.mark.parametrize("pattern,n_prbs,grid", [("comb4", 273, 273), ("comb2", 273, 273), ("comb4", 24, 52), ("comb2", 9, 52),
+                                                   ("type2", 17, 52), ("comb3", 8, 52), ("comb6", 30, 52), ("comb12", 16, 52),
+                                                   ("dense", 11, 52), ("comb4", 1, 52), ("comb2", 3, 52)])
+def test_tensor_fill_tiles_reproduce_the_operator(fill, pattern, n_prbs, grid):
+    """The bf16 operator tiles of the tensor-core fill, summed over their terms and placed at each tile's pilot window,
+    are exactly the float32 operator rows of the direct path (which test_fill_operator_matches_oracle pins to the oracle)."""
+    plan, hop1 = _plan(pattern, n_prbs, 4, fill=fill, grid=grid, start=grid - n_prbs)
+    i = plan.info
+    if not i.fill_tensor:
+        pytest.skip("no tensor-core fill for this geometry")
+    _, idx, coef = plan.tables()
+    a, kind, k0 = plan.fill_tensor_tables()
+    rows, terms = 12 * n_prbs, coef.shape[2]
+    assert i.fill_tensor_tiles == -(-rows // 96) and i.fill_tensor_k % 16 == 0
+    assert i.fill_tensor_terms == {1: 3, 2: 5, 3: 6}[i.fill_tensor_a_terms]
+    for g in range(i.n_cdm):
+        dense = np.zeros((rows, i.n_re + i.fill_tensor_k), dtype=np.float64)
+        for r in range(rows):
+            dense[r, idx[g, r]:idx[g, r] + terms] += coef[g, r].astype(np.float64)
+        for m in range(i.fill_tensor_tiles):
+            r0, r1 = 96 * m, min(rows, 96 * m + 96)
+            got = np.zeros_like(dense[r0:r1])
+            got[:, k0[m]:k0[m] + i.fill_tensor_k] = a[kind[m], g, :r1 - r0]
+            assert np.array_equal(got, dense[r0:r1]), (g, m)
+            assert not a[kind[m], g, r1 - r0:].any()
+            assert not dense[r0:r1, i.n_re:].any()
+
+
+def test_tensor_fill_is_refused_where_it_does_not_apply():
+    hop1 = synth.make_hop(52, 2, 8, [1], "comb4", 2)
+    hop2 = synth.make_hop(52, 30, 8, [8], "comb4", 2)
+    plan = estimator.make_plan(52, 14, 4, hop1, hop2, synth.make_config(30e3, "filter", True))
+    assert plan.info.fill_tensor == 0
+    with pytest.raises(NotImplementedError, match="two hops"):
+        plan.fill_tensor_tables()

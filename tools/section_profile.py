@@ -20,20 +20,23 @@ from srsran_ce_pytorch_b200 import _lib, estimator, synth  # noqa: E402
 from tools.sweep_bench import POINTS  # noqa: E402
 
 SECTIONS = ["wait stage", "cfo", "ls", "virt pilots", "wait writers", "fir(+blend)", "mean", "table+release",
-            "noise/rsrp", "ta (ifft)", "-", "W wait full", "W stream"]
+            "noise/rsrp", "ta: argmax", "-", "W wait full", "W stream", "ta: fill", "ta: fft", "ta: profile"]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--units", type=int, default=4096)
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="", help="comma-separated substring filters on the point name")
+    ap.add_argument("--ablate", type=int, default=0, help="SRSCE_DEBUG_ABLATE bits (2: no dense write = phase A alone)")
     a = ap.parse_args()
+    if a.ablate:
+        os.environ["SRSCE_DEBUG_ABLATE"] = str(a.ablate)
     lib = _lib.lib
     lib.srsce_prof_set_buffer.argtypes = [C.c_void_p]
     lib.srsce_prof_set_buffer.restype = C.c_int
     for point in POINTS:
         name, grid, nprb, s1, s2, pat, layers, sm, fill, share = point
-        if a.only and a.only not in name:
+        if a.only and not any(o in name for o in a.only.split(",")):
             continue
         n_cdm = (layers + 1) // 2
         hop1 = synth.make_hop(grid, 0, nprb, s1, pat, n_cdm)
@@ -59,12 +62,12 @@ def main():
         t = buf.cpu().double()
         ctas = int((t.sum(1) > 0).sum())
         per_unit = t[:ctas].sum(0) / a.units          # cycles per unit (every unit is counted by exactly one CTA)
-        est_total = float(per_unit[:11].sum())
+        est_total = float(per_unit[:11].sum() + per_unit[13:16].sum())
         print(f"== {name}: {ms:.3f} ms for {a.units} units, {ctas} CTAs, threads {plan.info.threads}, smem {plan.info.smem_bytes}")
         print("   estimator cycles/unit %.0f | writer cycles/unit %.0f" % (est_total, float(per_unit[11:13].sum())))
         for k, sname in enumerate(SECTIONS):
             if per_unit[k] > 0:
-                ref = est_total if k < 11 else float(per_unit[11:13].sum())
+                ref = float(per_unit[11:13].sum()) if k in (11, 12) else est_total
                 print(f"   {sname:14s} {float(per_unit[k]):9.0f} cyc  {100 * float(per_unit[k]) / ref:5.1f} %")
         del rx, pil, out, sc
         torch.cuda.empty_cache()
