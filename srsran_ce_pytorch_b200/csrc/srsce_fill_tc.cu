@@ -201,8 +201,9 @@ fill_tc_kernel(const __grid_constant__ FillTcDev F, const float2* __restrict__ h
       mbar_wait(&bars.d_full[stage], par);
       tc_fence_after();
       if (rows_here > 0) {
-        for (int u = half; u < u_here; u += 2) {
-          float v[G][4];
+        // software pipeline over this warp's units: the accumulator row of unit u + 2 is fetched from tensor memory
+        // while the rows of unit u stream out; the 32-row tile is double buffered so that one __syncwarp per unit suffices
+        auto fetch = [&](int u, float (&v)[G][4]) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             const int nl = (2 * g + 1 < LL) ? 2 : 1;
@@ -210,25 +211,31 @@ fill_tc_kernel(const __grid_constant__ FillTcDev F, const float2* __restrict__ h
             if (2 * g + 1 < LL) tmem_ld4(taddr, v[g]);
             else tmem_ld2(taddr, v[g]);
           }
+        };
+        float v[G][4];
+        if (half < u_here) fetch(half, v);
+        int tb = 0;
+        for (int u = half; u < u_here; u += 2, tb ^= 1) {
+          float2* const tl = tile + tb * (kFillEpiWarps * kTileRows * LL);
           tmem_ld_wait();
-          __syncwarp();                                      // the previous unit's rows have been streamed out of `tile`
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            tile[lane * LL + 2 * g] = make_float2(v[g][0], v[g][1]);
-            if (2 * g + 1 < LL) tile[lane * LL + 2 * g + 1] = make_float2(v[g][2], v[g][3]);
+            tl[lane * LL + 2 * g] = make_float2(v[g][0], v[g][1]);
+            if (2 * g + 1 < LL) tl[lane * LL + 2 * g + 1] = make_float2(v[g][2], v[g][3]);
           }
-          __syncwarp();
+          if (u + 2 < u_here) fetch(u + 2, v);
+          __syncwarp();                       // tile complete; also: every lane is done streaming the tile of unit u - 2 (same buffer)
           float2* const orow = out + ((u0 + u) * F.n_sc + F.band_sc0 + row0) * (14 * LL);
           if (rows_here == 32) {
             if (lane_on) {
               float4* dst = reinterpret_cast<float4*>(orow + (long long)my_rs * (14 * LL) + e0);
               if constexpr (LL == 4 || LL == 2)
-                stream_full_tile<LL, false>(reinterpret_cast<const float4*>(tile + my_rs * LL + l0), dst, on0, one, one);
+                stream_full_tile<LL, false>(reinterpret_cast<const float4*>(tl + my_rs * LL + l0), dst, on0, one, one);
               else
-                stream_full_tile_odd<LL, false>(tile + my_rs * LL + l0, tile + my_rs * LL + l1, dst, on0, on1, one, one);
+                stream_full_tile_odd<LL, false>(tl + my_rs * LL + l0, tl + my_rs * LL + l1, dst, on0, on1, one, one);
             }
           } else {
-            stream_rows<LL>(tile, orow, rows_here, lane, F.sym0, F.sym1);
+            stream_rows<LL>(tl, orow, rows_here, lane, F.sym0, F.sym1);
           }
         }
       }

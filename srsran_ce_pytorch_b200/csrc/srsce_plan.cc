@@ -328,7 +328,7 @@ static void build_fill_tc(Plan& p, int n_hops) {
   f.off_a = 0;
   f.off_b = up128(f.n_kinds * G * n_a * f.a_block_bytes);
   f.off_tile = f.off_b + up128(2 * f.b_stage_bytes);
-  f.off_bar = f.off_tile + kFillEpiWarps * kTileRows * SRSCE_MAX_LAYERS * 8;
+  f.off_bar = f.off_tile + 2 * kFillEpiWarps * kTileRows * SRSCE_MAX_LAYERS * 8;   // double-buffered 32-row tile per epilogue warp
   f.smem_bytes = f.off_bar + 128;
   // (the MMA reads 128 operator rows where a block holds 96: the 32 phantom rows of the last block fall into the X
   //  stages behind it, 64 * k_tile bytes at most, always inside the allocation)
