@@ -22,19 +22,31 @@ __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2
 // Writer hot loop for a full 32-row tile of a 14-symbol grid with LL (2 or 4) layers: every lane owns one 16-byte
 // store slot (symbol, layer pair) and walks the rows with compile-time strides, so each row costs one LDS.128 and
 // one STG.128 with the offsets folded into the instructions.  (32 / cols) rows are covered per warp pass.
+// The shared loads are issued kStreamBatch rows at a time ahead of their stores: the writer warps share the SM's
+// in-order load/store pipe with the estimator warps, and while the stores drain at HBM speed a shared load waits
+// ~1 k cycles in that pipe -- the bytes a writer warp has in flight per such round trip set its store rate.
+constexpr int kStreamBatch = 16;
 template <int LL, bool ROT>
 __device__ __forceinline__ void stream_full_tile(const float4* __restrict__ src, float4* __restrict__ dst, bool on,
                                                  float2 rot0, float2 rot1) {
   constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = (kTileRows + kRowsPerPass - 1) / kRowsPerPass;
   static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
+  constexpr int kB = kPasses < kStreamBatch ? kPasses : kStreamBatch;
+  static_assert(kPasses % kB == 0, "passes must split evenly into batches");
 #pragma unroll
-  for (int p = 0; p < kPasses; ++p) {
-    float4 v = on ? src[p * (kRowsPerPass * LL / 2)] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ROT) {
-      const float2 a = cmul(make_float2(v.x, v.y), rot0), b = cmul(make_float2(v.z, v.w), rot1);
-      v = make_float4(a.x, a.y, b.x, b.y);
+  for (int p0 = 0; p0 < kPasses; p0 += kB) {
+    float4 v[kB];
+#pragma unroll
+    for (int k = 0; k < kB; ++k) v[k] = on ? src[(p0 + k) * (kRowsPerPass * LL / 2)] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kB; ++k) {
+      float4 w = v[k];
+      if (ROT) {
+        const float2 a = cmul(make_float2(w.x, w.y), rot0), b = cmul(make_float2(w.z, w.w), rot1);
+        w = make_float4(a.x, a.y, b.x, b.y);
+      }
+      __stcs(dst + (p0 + k) * (kRowsPerPass * kCols), w);
     }
-    __stcs(dst + p * (kRowsPerPass * kCols), v);
   }
 }
 

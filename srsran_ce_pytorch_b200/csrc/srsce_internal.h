@@ -29,7 +29,7 @@ constexpr int cta_threads(int na, bool two_hops) { return na + 32 * writer_warps
 constexpr int kTileRows = 32;         // subcarrier rows a warp expands per tile (one per lane)
 constexpr int kMaxFillTerms = 8;      // widest CNN operator row the kernel accepts
 constexpr int kCnnEdgeRows = 2 * kNRE; // band rows at either end whose CNN operator rows are looked up individually
-constexpr int kMiscBytes = 5504;      // shared-memory slot of the kernel's small tables / reduction scratch ...
+constexpr int kMiscBytes = 5616;      // shared-memory slot of the kernel's small tables / reduction scratch ...
 constexpr int kHopScratchBytes = 2176; // ... followed by one slot per hop (rotation tables, delay profile, edge-pilot scratch)
 
 // One entry of the per-PRB interpolation table (fill_ch_est_cdm, ce_rule_tensorized.py:311-340):
@@ -78,6 +78,7 @@ struct PlanDev {
   int32_t hall_bufs;       // 1: writers and the next unit's FIR alternate on one pilot buffer; 2: double buffered
   int32_t y_bufs;          // staging buffers of the received pilot REs: 2 = fetched a whole unit ahead, 1 = during the IFFT
   int32_t fir_per_group;   // FIR input (ext) holds one CDM group (<= 2 layers) at a time instead of all layers
+  int32_t ta_radix4;       // time-alignment transform: 1 = radix-4 passes + twiddle table (light phase A), 0 = register-blocked radix 8
   // shared-memory carve-up (byte offsets from the dynamic smem base)
   int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;
   int32_t ext_hop;         // complex64 elements of one hop's FIR-input region inside ext

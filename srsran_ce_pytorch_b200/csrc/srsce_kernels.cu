@@ -53,6 +53,8 @@ struct Misc {
   float cnn_coef[2][kNRE][kMaxFillTerms];
   int32_t cnn_idx0[2][kNRE];
   ColInfo col[2][SRSCE_MAX_SYMBOLS * SRSCE_MAX_LAYERS];   // one store-slot table per hall buffer
+  int32_t re_inv[kNRE];                                   // RE position inside a PRB -> pilot ordinal of the LAST CDM group (-1: none)
+  float2 w8[8];                                           // e^{+j 2 pi k / 8}: last (fused) stage of the TA transform
 };
 struct HopScratch {        // per hop, after Misc
   float2 rot_neg[SRSCE_MAX_SYMBOLS];
@@ -175,6 +177,89 @@ __device__ float2 virtual_pilot(int nv, double mx, double den, const float* mod,
   return make_float2(float(amp * cs), float(amp * sn));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Time-alignment transform (:674-698): inverse (e^{+j...}) decimation-in-frequency FFT of `nl` vectors of length
+// M = 512 * RF (RF = 2, 4, 8 <=> M = 1024, 2048, 4096) as three register-blocked radix-8 passes at strides M/8, M/64
+// and RF; the last stage (radix RF on RF consecutive elements) is not run as a pass: only 288 bins are ever looked
+// at, so each of them is evaluated directly from its RF inputs when the delay profile is formed.
+//   pass 1 reads the pilots straight from `hall` (zero padded / zero stuffed on the fly): no separate fill pass
+//   twiddles are computed (one sincospif of an exact argument per task, powers by multiplication), not loaded
+// Every element therefore makes three shared-memory round trips (the radix-4 version made 6-7) with 8-point
+// butterflies in registers.  Vectors live in `ext` with one pad element per 8 (index i at i + i / 8) so that pass 3's
+// short strides fall on distinct banks.  After the passes, bin k = d1 + 8 d2 + 64 d3 + 512 d4 is
+//   sum_{m < RF} x[d1 * M/8 + d2 * M/64 + d3 * RF + m] * e^{+j 2 pi m d4 / RF}.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fft_pad(int i) { return i + (i >> 3); }
+
+// 4-point inverse DFT in place: y[r] = sum_m a[m] * (+j)^(m r)
+__device__ __forceinline__ void bf4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+  const float2 d = csub(a1, a3);
+  const float2 t3 = make_float2(-d.y, d.x);              // +j * (a1 - a3)
+  a0 = cadd(t0, t2);
+  a1 = cadd(t1, t3);
+  a2 = csub(t0, t2);
+  a3 = csub(t1, t3);
+}
+// 8-point inverse DFT in registers, natural order: radix 2 x radix 4.
+__device__ __forceinline__ void fft8(float2 (&x)[8]) {
+  constexpr float h = 0.70710678118654752f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 u = cadd(x[j], x[j + 4]), v = csub(x[j], x[j + 4]);
+    x[j] = u;
+    x[j + 4] = v;
+  }
+  x[5] = cmul(x[5], make_float2(h, h));        // w8^1
+  x[6] = make_float2(-x[6].y, x[6].x);         // w8^2 = +j
+  x[7] = cmul(x[7], make_float2(-h, h));       // w8^3
+  bf4(x[0], x[1], x[2], x[3]);                 // -> y[0], y[2], y[4], y[6]
+  bf4(x[4], x[5], x[6], x[7]);                 // -> y[1], y[3], y[5], y[7]
+  const float2 y1 = x[4], y2 = x[1], y3 = x[5], y4 = x[2], y5 = x[6], y6 = x[3];
+  x[1] = y1; x[2] = y2; x[3] = y3; x[4] = y4; x[5] = y5; x[6] = y6;
+}
+
+
+// One radix-8 task: x[m] (already loaded, natural order) -> butterfly -> twiddle by w^(r), w = e^{+j pi two_j_over_n}
+__device__ __forceinline__ void fft8_twiddled(float2 (&x)[8], float two_j_over_n) {
+  fft8(x);
+  float sn, cs;
+  sincospif(two_j_over_n, &sn, &cs);
+  const float2 w1 = make_float2(cs, sn), w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+  x[1] = cmul(x[1], w1);
+  x[2] = cmul(x[2], w2);
+  x[3] = cmul(x[3], w3);
+  x[4] = cmul(x[4], w4);
+  x[5] = cmul(cmul(x[5], w4), w1);
+  x[6] = cmul(cmul(x[6], w4), w2);
+  x[7] = cmul(cmul(x[7], w4), w3);
+}
+
+// Passes 2 and 3 over `nl` padded vectors of length M (Mp = M + M / 8 elements apart) in s[].
+template <int NA>
+__device__ __forceinline__ void fft_pass23(float2* s, int nl, int log2M) {
+  const int tid = threadIdx.x, Mp = (1 << log2M) + (1 << (log2M - 3));
+  const int log2t = log2M - 3;                                    // tasks per vector in every pass = M / 8
+#pragma unroll 1
+  for (int pass = 2; pass <= 3; ++pass) {
+    const int log2q = log2M - 3 * pass;                           // stride of the pass: M / 64, then RF = M / 512
+    for (int t = tid; t < (nl << log2t); t += NA) {
+      const int l = t >> log2t, rem = t & ((1 << log2t) - 1);
+      const int blk = rem >> log2q, j = rem & ((1 << log2q) - 1);
+      float2* const v = s + l * Mp;
+      const int i0 = (blk << (log2q + 3)) + j;
+      float2 x[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) x[m] = v[fft_pad(i0 + (m << log2q))];
+      fft8_twiddled(x, float(2 * j) / float(8 << log2q));         // w = e^{+j 2 pi j / n}, n = 8 q (exact in float)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[fft_pad(i0 + (r << log2q))] = x[r];
+    }
+    sync_a<NA>();
+  }
+}
+
+// ---- the radix-4 transform of round 1, kept for the plans whose phase A is light (see PlanDev::ta_radix4)
 // Where output bin k of the in-place decimation-in-frequency transform of length M ends up.
 __device__ __forceinline__ int dif_position(int k, int M) {
   int pos = 0, n = M;
@@ -312,6 +397,17 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     m.re_pos[k / kNRE][k % kNRE] = P.re_pos[k / kNRE][k % kNRE];
     m.cnn_idx0[k / kNRE][k % kNRE] = P.cnn_idx0[k / kNRE][k % kNRE];
   }
+  if (tid < 8) {
+    float sn, cs;
+    sincospif(0.25f * float(tid), &sn, &cs);
+    m.w8[tid] = make_float2(cs, sn);
+  }
+  if (tid < kNRE) {
+    int r = -1;
+    for (int k = 0; k < R; ++k)
+      if (P.re_pos[G - 1][k] == tid) r = k;
+    m.re_inv[tid] = r;
+  }
   if (tid == 0) m.r_magic = (R == 1) ? 0u : static_cast<unsigned>(((1ull << 32) + static_cast<unsigned>(R) - 1) / static_cast<unsigned>(R));
   for (int k = tid; k < 2 * kNRE * kMaxFillTerms; k += kThreads)
     (&m.cnn_coef[0][0][0])[k] = (&P.cnn_coef[0][0][0])[k];
@@ -367,18 +463,15 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       rot_c[unit * P.n_sym + tid] = make_float2(float(cs), float(sn));
     }
   };
-  stage_unit(blockIdx.x, ystage);
-  cp_async_commit();
-
-  int it = 0;
-  for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-    if (h_in != nullptr) {
-      // fill-only launch (srsce_fill, direct implementation): the smoothed pilots [hop][N][L] of the unit are an
-      // input; transpose them into hall ([hop][layer][N]) and hand them to the writer warps -- phase B alone, i.e.
-      // fill_ch_est_cdm (:237-354 / ce_dl_cnn.py:233-322) for every CDM group of every hop
-      const int hb = (P.hall_bufs == 2) ? (it & 1) : 0;
+  if (h_in != nullptr) {
+    // fill-only launch (srsce_fill, direct implementation): the smoothed pilots [hop][N][L] of every unit are an
+    // input; transpose them into hall ([hop][layer][N]) and hand them to the writer warps -- phase B alone, i.e.
+    // fill_ch_est_cdm (:237-354 / ce_dl_cnn.py:233-322) for every CDM group of every hop
+    int itf = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++itf) {
+      const int hb = (P.hall_bufs == 2) ? (itf & 1) : 0;
       float2* const hdst = hall0 + hb * (n_hops * L * N);
-      if (it >= P.hall_bufs) bar_sync(kBarEmpty + hb, kCtaThreads);
+      if (itf >= P.hall_bufs) bar_sync(kBarEmpty + hb, kCtaThreads);
       const float2* __restrict__ hu = h_in + u * ((long long)n_hops * N * L);
       for (int idx = tid; idx < n_hops * N * L; idx += kThreads) {
         const int hh = idx / (N * L), rem = idx - hh * (N * L), i = rem / L, l = rem - i * L;
@@ -386,8 +479,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       }
       build_store_table(m.col[hb]);
       bar_arrive(kBarFull + hb, kCtaThreads);
-      continue;
     }
+  } else {
+  stage_unit(blockIdx.x, ystage);
+  cp_async_commit();
+
+  int it = 0;
+  for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
     const float2* __restrict__ pu = pilots + (u / pilot_share) * ((long long)N * ST * L);
     cp_async_wait_all();                                      // this unit's pilot REs have landed ...
     sync_a<NA>();                                                 // ... for every estimator thread
@@ -707,9 +805,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
         stage_unit(u + gridDim.x, ystage);                     // the next unit's arrive while the IFFT below runs
         cp_async_commit();
       }
+      PROF_MARK(tid == 0, 10);
 
-      // ---- time alignment (:674-698): IFFT of every (hop, layer) vector, fft_layers at a time
+      // ---- time alignment (:674-698): IFFT of every (hop, layer) vector, fft_layers at a time; every thread keeps
+      //      the delay-profile bins it owns in registers across the rounds (layers summed in order, per hop)
       {
+        if (P.ta_radix4) {
+          // radix-4 passes over a dense twiddle table (round 1): slower by itself, but measured gentler on the writer warps
+          // when phase A is light -- the planner's choice (srsce_plan.cc)
         const int M = P.fft_size, log2M = 31 - __clz(M);
         const int* posl = m.re_pos[G - 1];
         const int n_vec = n_hops * L;
@@ -745,6 +848,77 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           }
           sync_a<NA>();
           PROF_MARK(tid == 0, 15);
+        }
+        } else {
+        const int M = P.fft_size, log2M = 31 - __clz(M), log2rf = log2M - 9, Mp = M + (M >> 3);
+        const int n_vec = n_hops * L;
+        constexpr int kBins = (2 * SRSCE_TA_WINDOW + NA - 1) / NA;
+        float ta_acc[kBins][2];
+#pragma unroll
+        for (int k = 0; k < kBins; ++k) ta_acc[k][0] = ta_acc[k][1] = 0.f;
+        const int pos0 = m.re_pos[G - 1][0];
+        for (int vb = 0; vb < n_vec; vb += P.fft_layers) {
+          const int nl = min(P.fft_layers, n_vec - vb);
+          // pass 1 (stride M / 8): one (vector, j) task per thread and step, inputs straight from hall
+          for (int t = tid; t < (nl << (log2M - 3)); t += kThreads) {
+            const int l = t >> (log2M - 3), j = t & ((M >> 3) - 1);
+            const float2* const hv = hall + (vb + l) * N;              // vector v = hop * L + layer: hall is [hop][layer][N]
+            float2 x[8];
+            if (P.fft_regular) {
+#pragma unroll
+              for (int mm = 0; mm < 8; ++mm) {
+                const int n = j + mm * (M >> 3);
+                x[mm] = (n < N) ? hv[n] : make_float2(0.f, 0.f);
+              }
+            } else {
+              // zero-stuffed 4096-point input: sample n sits pos0 subcarriers above the first pilot's PRB origin
+#pragma unroll
+              for (int mm = 0; mm < 8; ++mm) {
+                const int sc = j + mm * (M >> 3) + pos0, q = int(__umulhi(unsigned(sc), 357913942u));   // sc / 12
+                const int r = m.re_inv[sc - q * kNRE], i = q * R + r;
+                x[mm] = (r >= 0 && i < N) ? hv[i] : make_float2(0.f, 0.f);
+              }
+            }
+            fft8_twiddled(x, float(2 * j) / float(M));
+            float2* const dst = ext + l * Mp;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) dst[fft_pad(j + r * (M >> 3))] = x[r];
+          }
+          sync_a<NA>();
+          PROF_MARK(tid == 0, 13);
+          fft_pass23<NA>(ext, nl, log2M);
+          PROF_MARK(tid == 0, 14);
+          // delay profile: the bins of the two windows, each from the RF inputs of its last butterfly
+#pragma unroll
+          for (int k = 0; k < kBins; ++k) {
+            const int t = tid + k * kThreads;
+            if (t < 2 * SRSCE_TA_WINDOW) {
+              const int bin = ((t < SRSCE_TA_WINDOW) ? t : SRSCE_TA_FFT - 2 * SRSCE_TA_WINDOW + t) & (M - 1);
+              const int d1 = bin & 7, d2 = (bin >> 3) & 7, d3 = (bin >> 6) & 7, d4 = bin >> 9;
+              const int base = fft_pad(d1 * (M >> 3) + d2 * (M >> 6) + (d3 << log2rf));   // RF <= 8 elements: one pad group
+              const int wstep = d4 << (3 - log2rf);                 // e^{+j 2 pi m d4 / RF} = w8[(m d4 8 / RF) mod 8]
+              for (int l = 0; l < nl; ++l) {
+                const float2* const e = ext + l * Mp + base;
+                float2 z = e[0];
+                for (int mm = 1; mm < (1 << log2rf); ++mm) z = cadd(z, cmul(e[mm], m.w8[(mm * wstep) & 7]));
+                const float pw = z.x * z.x + z.y * z.y;
+                if (TWO_HOPS && vb + l >= L) ta_acc[k][1] += pw;
+                else ta_acc[k][0] += pw;
+              }
+            }
+          }
+          if (vb + P.fft_layers < n_vec) sync_a<NA>();                   // the next round overwrites ext
+        }
+#pragma unroll
+        for (int k = 0; k < kBins; ++k) {
+          const int t = tid + k * kThreads;
+          if (t < 2 * SRSCE_TA_WINDOW) {
+            hsx[0].prof[t] = ta_acc[k][0];
+            if (TWO_HOPS) hsx[1].prof[t] = ta_acc[k][1];
+          }
+        }
+        sync_a<NA>();
+        PROF_MARK(tid == 0, 15);
         }
         if (warp < n_hops) {
           // first maximum of each window; ties keep the lower index, as torch.max / np.argmax
@@ -794,6 +968,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
     }
     // (the barrier at the top of the next unit orders these reads of m.acc before it is cleared)
   }
+  }  // estimator loop (not a fill-only launch)
   PROF_FLUSH(tid == 0, 0);
   } else {
   // ================================== writer warps ============================================
@@ -822,11 +997,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
       const ColInfo mine = colb[my_c];
       const bool pair = (VEC == 2) && ((L & 1) == 0);      // both elements of a slot are adjacent layers of one symbol
 
-      for (int row0 = wb * kTileRows; row0 < ((dbg & 2) ? 0 : n_sc); row0 += kWarpsB * kTileRows) {
+      // interpolate the 32 rows starting at row0 into a tile ([hop][row][layer]); returns the per-hop in-band row masks
+      auto interp_tile = [&](int row0, float2* tile0, unsigned& in1, unsigned& in2) {
         const int row = row0 + lane;
-        const int rows_here = min(kTileRows, n_sc - row0);
-        unsigned in1 = 0, in2 = 0;
-        __syncwarp();
+        in1 = in2 = 0;
 #pragma unroll
         for (int hh = 0; hh < n_hops; ++hh) {
           const HopDev& H = P.hop[hh];
@@ -882,8 +1056,11 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           }
         }
-        __syncwarp();
-
+      };
+      // stream the rows of a finished tile to the grid (or the compact output)
+      auto emit_tile = [&](int row0, const float2* tile0, unsigned in1, unsigned in2) {
+        const int row = row0 + lane;
+        const int rows_here = min(kTileRows, n_sc - row0);
         if (out_c != nullptr) {
           // compact output [unit][hop][subcarrier][layer]: every lane writes the row it interpolated
           if (row < n_sc) {
@@ -895,7 +1072,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
               for (int l = 0; l < L; ++l) __stcs(d + l, have ? t[l] : make_float2(0.f, 0.f));
             }
           }
-          continue;
+          return;
         }
 
         if (fast) {
@@ -975,6 +1152,16 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             }
           }
         }
+      };
+      const int row_end = (dbg & 2) ? 0 : n_sc, row_step = kWarpsB * kTileRows;
+      // (Tried: a software-pipelined variant that fetches the next tile's pilots before streaming this one, into a second
+      //  tile buffer -- no gain on B200)
+      for (int row0 = wb * kTileRows; row0 < row_end; row0 += row_step) {
+        unsigned in1, in2;
+        __syncwarp();
+        interp_tile(row0, tile0, in1, in2);
+        __syncwarp();
+        emit_tile(row0, tile0, in1, in2);
       }
     }
     PROF_MARK(wb == 0 && lane == 0, 12);

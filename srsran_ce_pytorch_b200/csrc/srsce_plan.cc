@@ -616,7 +616,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       v.fft_layers = slim ? std::min(fft_default, 2) : fft_default;
       v.ext_hop = fir_len * ext_layers;                              // FIR input incl. virtual pilots and zero margins, per hop
       int ext = n_hops * v.ext_hop;                                 // (also the scratch of the CNN blend: N * layers <= ext_hop)
-      ext = std::max(ext, v.fft_layers * v.fft_size);               // FFT scratch
+      ext = std::max(ext, v.fft_layers * (v.fft_size + v.fft_size / 8));   // FFT scratch: one pad element per 8 (bank spread)
       const int tile_elems = writer_warps(na, n_hops == 2) * kTileRows * L * n_hops;
       v.ext_elems = ext;
       v.est_threads = na;
@@ -637,6 +637,14 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     // (0.75 vs 0.73, 0.69 vs 0.64, 0.80 vs 0.78, 0.52 vs 0.50): their phase A is long enough that a single CTA's
     // writers starve between hand-overs.
     const bool light = n_hops == 1 && s_total == 1 && L % 2 == 0 && v.fft_regular;
+    // Time-alignment transform.  The register-blocked radix-8 version (3 shared-memory round trips per element, no
+    // twiddle loads) takes a third of the radix-4 version's time and lifts every phase-A-bound geometry (same box,
+    // fraction of the HBM peak: comb-2 0.65 -> 0.75, type-2 mask 0.53 -> 0.77, S = 4 0.59 -> 0.63, ce_dl_cnn fill
+    // 0.83 -> 0.86, two-hop shapes 0.52 -> 0.72).  The writer-bound headline family (one hop, one pilot symbol, four
+    // ports on a comb-4: config 2 and its narrow-band hops) measures 2.5-3.7 % SLOWER with it (config 2 at bench
+    // size: 0.888 -> 0.856) although its phase A is shorter, so those plans keep the radix-4 passes; with two ports
+    // or one the radix-8 passes are level or ahead.  A measured rule like the CTA-shape rule above, not a model.
+    v.ta_radix4 = (light && G == 2 && v.fft_size == 1024 && d.fill == SRSCE_FILL_LINEAR) ? 1 : 0;
     if (!(light && layout(512, 1, 1, false) <= one_cta_l1_budget) &&
         layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
         layout(512, 1, 1, false) > 227 * 1024 && layout(512, 1, 1, true) > 227 * 1024)

@@ -20,7 +20,7 @@ from srsran_ce_pytorch_b200 import _lib, estimator, synth  # noqa: E402
 from tools.sweep_bench import POINTS  # noqa: E402
 
 SECTIONS = ["wait stage", "cfo", "ls", "virt pilots", "wait writers", "fir(+blend)", "mean", "table+release",
-            "noise/rsrp", "ta: argmax", "-", "W wait full", "W stream", "ta: fill", "ta: fft", "ta: profile"]
+            "noise/rsrp", "ta: argmax", "stage issue", "W wait full", "W stream", "ta: pass 1", "ta: pass 2-3", "ta: profile"]
 
 
 def main():
