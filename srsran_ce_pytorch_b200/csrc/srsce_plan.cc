@@ -599,7 +599,10 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   //      stretch between "writers done" and "next FIR done" is shortest when both CDM groups are de-spread ahead).
   //   D  the same with the slim footprint (the largest geometries).
   //   E  D without a staging buffer: the pilot REs are read from the received grid where they are used (dense
-  //      masks with several pilot symbols; everything with n_sc <= 4096 and <= 4 layers fits).
+  //      masks with several pilot symbols).  What does NOT fit even so: two-hop plans whose smoothed pilots of both
+  //      hops (2 * N * L * 8 bytes) leave no room for the rest -- in practice the dense mask (12 pilots per PRB) on
+  //      two hops at 273 PRB with >= 3 layers or 341 PRB with >= 2 layers (host sweep of 1 120 geometries: those 20
+  //      and nothing else).  They fail with SRSCE_ERR_UNSUPPORTED; DESIGN.md section 1 lists the envelope.
   //   Measured on B200 (comb-2, 273 PRB): single staging buffer 0.60 (C) / 0.59 (D), two staging buffers 0.58 / 0.57,
   //   smoothed pilots double buffered 0.50-0.54 of the HBM peak -- phase A re-reads the pilots through L1, the
   //   gather of the next unit pollutes L1 unless it is issued after the noise estimate, and L1 is what shared

@@ -23,9 +23,9 @@ for ln in sass:
         continue
     if not on:
         continue
-    m = re.search(r'//## File ".*", line (\d+)', ln)
+    m = re.search(r'//## File "(.*)", line (\d+)', ln)
     if m:
-        cur = int(m.group(1))
+        cur = (m.group(1), int(m.group(2)))
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append((cur, ln.strip()))
@@ -40,8 +40,11 @@ for (ln, _), r in zip(lines, data):
     by_line[ln] += int(r[wi] or 0)
     inst_line[ln] += int(r[ii] or 0)
 tot, toti = sum(by_line.values()), sum(inst_line.values())
-src = (root / "srsran_ce_pytorch_b200" / "csrc" / "srsce_kernels.cu").read_text().splitlines()
+files = {}
 print(f"total samples {tot}, warp instructions {toti}")
-for ln, s in sorted(by_line.items(), key=lambda kv: -kv[1])[:top]:
-    text = src[ln - 1].strip()[:100] if ln else "?"
-    print(f"{ln or 0:5d} {100 * s / tot:5.1f}% samp {100 * inst_line[ln] / toti:5.1f}% inst  {text}")
+for key, s in sorted(by_line.items(), key=lambda kv: -kv[1])[:top]:
+    f, ln = key if key else ("?", 0)
+    if f not in files:
+        files[f] = Path(f).read_text().splitlines() if os.path.exists(f) else []
+    text = files[f][ln - 1].strip()[:100] if ln and ln <= len(files[f]) else "?"
+    print(f"{os.path.basename(f)}:{ln:<5d} {100 * s / tot:5.1f}% samp {100 * inst_line[key] / toti:5.1f}% inst  {text}")
