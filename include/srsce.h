@@ -131,7 +131,8 @@ int srsce_plan_fill_tensor_tables(const srsce_plan* plan, uint16_t* a_tiles, int
  *             + sc*rx_strides[1] + sym*rx_strides[2]   (strides in complex64 elements; the
  *             reference layout [n_sc, n_sym] is {n_sc*n_sym, n_sym, 1})
  *   pilots    complex64 [n_units / pilot_share][n_re][n_dmrs_total][n_layers] contiguous; unit u
- *             reads block u / pilot_share (the rx antennas of one UE share its pilots)
+ *             reads block u / pilot_share (the rx antennas of one UE share its pilots); 16-byte aligned
+ *             when n_layers is even (8-byte otherwise)
  *   beta      beta_dmrs
  *   ch_est    complex64 [n_units][n_sc][n_sym][n_layers] contiguous, fully overwritten
  *   scalars   double [n_units][6]: noise_est, rsrp, epre, time_alignment (s), cfo_hz, cfo_valid

@@ -117,6 +117,8 @@ int srsce_estimate(const srsce_plan* plan, const void* rx_grid, const int64_t rx
       (reinterpret_cast<uintptr_t>(pilots) & 7u) || (reinterpret_cast<uintptr_t>(scalars) & 7u))
     return fail(SRSCE_ERR_INVALID, "buffers must be aligned (ch_est 16 B, others 8 B)");
   try {
+    if ((plan->impl.dev.n_layers & 1) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u))
+      return fail(SRSCE_ERR_INVALID, "pilots must be 16-byte aligned when the layer count is even (the kernel loads layer pairs)");
     std::string err;
     const int rc = srsce::launch_estimate(plan->impl, rx_grid, rx_strides, pilots, pilot_share, beta, ch_est, scalars,
                                           n_units, stream, &g_launches, err);
@@ -141,6 +143,8 @@ int srsce_estimate_compact(const srsce_plan* plan, const void* rx_grid, const in
       (reinterpret_cast<uintptr_t>(scalars) & 7u))
     return fail(SRSCE_ERR_INVALID, "buffers must be 8-byte aligned");
   try {
+    if ((plan->impl.dev.n_layers & 1) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u))
+      return fail(SRSCE_ERR_INVALID, "pilots must be 16-byte aligned when the layer count is even (the kernel loads layer pairs)");
     std::string err;
     const int rc = srsce::launch_estimate(plan->impl, rx_grid, rx_strides, pilots, pilot_share, beta, nullptr, scalars,
                                           n_units, stream, &g_launches, err, ch_sc, sym_rot);
@@ -165,6 +169,8 @@ int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const i
       (reinterpret_cast<uintptr_t>(rx_index) & 7u))
     return fail(SRSCE_ERR_INVALID, "buffers must be aligned (ch_est 16 B, others 8 B)");
   try {
+    if ((plan->impl.dev.n_layers & 1) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u))
+      return fail(SRSCE_ERR_INVALID, "pilots must be 16-byte aligned when the layer count is even (the kernel loads layer pairs)");
     std::string err;
     const int rc = srsce::launch_estimate(plan->impl, rx_grids, rx_strides, pilots, pilot_share, beta, ch_est, scalars,
                                           n_units, stream, &g_launches, err, nullptr, nullptr, rx_index);

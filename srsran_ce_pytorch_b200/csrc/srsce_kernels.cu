@@ -129,6 +129,20 @@ __device__ __forceinline__ void block_sum(Misc& m, double (&v)[K]) {
   sync_a<NA>();
 }
 
+// The pilots of the two layers of a CDM group are adjacent in memory ([pilot][symbol][layer]).  A thread owns a pilot, so
+// its loads are 128 bytes apart from its neighbours': every load instruction touches 32 cache lines whatever its width,
+// and with an even layer count one 16-byte load (both layers) halves the L1 wavefronts of the pilot passes.
+__device__ __forceinline__ void ld_pilot_pair(const float2* __restrict__ pp, bool vec, bool two, float2& a, float2& b) {
+  if (vec) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(pp));
+    a = make_float2(v.x, v.y);
+    b = make_float2(v.z, v.w);
+  } else {
+    a = __ldg(pp);
+    b = two ? __ldg(pp + 1) : make_float2(0.f, 0.f);
+  }
+}
+
 // Subcarrier of pilot i of CDM group g inside a hop band.
 // (i / R as one IMAD.HI: r_magic = ceil(2^32 / R) is exact for i < 2^16, 2 <= R <= 12; R == 1 has no 32-bit magic.
 //  Written with __umulhi on purpose: the 64-bit form `(u64(i) * magic) >> 32` followed by `q * R` was mis-folded by
@@ -389,6 +403,7 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   const int n_sc = P.n_sc, row_elems = P.row_elems, cols = P.cols;
   const int ylen = G * N * ST;
   const bool filt = P.smoothing == SRSCE_SMOOTH_FILTER;
+  const bool pvec = (L & 1) == 0;                          // 16-byte pilot loads (the ABI asks for 16-byte aligned pilots then)
 
   // plan tables that are indexed per lane go to shared memory once per CTA
   for (int k = tid; k < SRSCE_MAX_TAPS; k += kThreads) m.taps[k] = P.taps[k];
@@ -526,10 +541,13 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
             for (int i = tid; i < N; i += kThreads) {
               const float2 y0 = ld_y(H, g, i, 0), y1 = ld_y(H, g, i, 1);
               const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
+              float2 p0[2], p1[2];
+              ld_pilot_pair(pp, pvec, 2 * g + 1 < L, p0[0], p0[1]);
+              ld_pilot_pair(pp + L, pvec, 2 * g + 1 < L, p1[0], p1[1]);
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 if (2 * g + k < L) {
-                  const float2 x0 = cmul_conj(y0, __ldg(pp + k)), x1 = cmul_conj(y1, __ldg(pp + L + k));
+                  const float2 x0 = cmul_conj(y0, p0[k]), x1 = cmul_conj(y1, p1[k]);
                   c[g][k] = cadd(c[g][k], cmul_conj(x1, x0));      // conj(x0) * x1
                 }
               }
@@ -600,12 +618,14 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                   const float2* pp = pu + ((long long)i * ST + col0) * L + 2 * g;
                   for (int s = 0; s < S; ++s) {
                     const float2 y = ld_y(H, g, i, s);
+                    float2 pa, pb;
+                    ld_pilot_pair(pp + s * L, pvec, two, pa, pb);
                     epre_part[hh] += y.x * y.x + y.y * y.y;
-                    float2 x0 = cmul_conj(y, __ldg(pp + s * L));
+                    float2 x0 = cmul_conj(y, pa);
                     if (derot) x0 = cmul(x0, hsx[hh].rot_neg[s]);
                     a0 = cadd(a0, x0);
                     if (two) {
-                      float2 x1 = cmul_conj(y, __ldg(pp + s * L + 1));
+                      float2 x1 = cmul_conj(y, pb);
                       if (derot) x1 = cmul(x1, hsx[hh].rot_neg[s]);
                       a1 = cadd(a1, x1);
                     }
@@ -772,8 +792,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
                 const float2 h1 = two ? hbuf[(2 * g + 1) * N + i] : make_float2(0.f, 0.f);
                 for (int s = 0; s < S; ++s) {
                   const float2 y = ld_y(H, g, i, s);
-                  float2 e = cmul(__ldg(pp + s * L), derot ? cmul(h0, hsx[hh].rot_pos[s]) : h0);
-                  if (two) e = cadd(e, cmul(__ldg(pp + s * L + 1), derot ? cmul(h1, hsx[hh].rot_pos[s]) : h1));
+                  float2 pa, pb;
+                  ld_pilot_pair(pp + s * L, pvec, two, pa, pb);
+                  float2 e = cmul(pa, derot ? cmul(h0, hsx[hh].rot_pos[s]) : h0);
+                  if (two) e = cadd(e, cmul(pb, derot ? cmul(h1, hsx[hh].rot_pos[s]) : h1));
                   const float2 d = csub(y, cscale(e, beta));
                   noise_part += d.x * d.x + d.y * d.y;
                 }
