@@ -782,6 +782,25 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
           const bool derot = S >= 2 && P.cfo_compensate;
           const float2* const hbuf = hall + hh * L * N;
           float noise_part = 0.f, rsrp_part = 0.f;
+          if (pvec && S >= 2) {
+            // Several pilot symbols, even layer count: one thread per 16-byte chunk (pilot, symbol, CDM group) in memory
+            // order, so that a warp's loads are 512 contiguous bytes (4 cache lines) instead of 32 lines -- the residual
+            // is elementwise, only the order of the float32 partial sums changes.  (The same mapping for the CFO
+            // correlation and the LS step needs shuffles to pair / sum the symbols of a pilot and measured slower.)
+            const int per_pilot = S * G, total = N * per_pilot;
+            for (int c = tid; c < total; c += kThreads) {
+              const int i = c / per_pilot, r = c - i * per_pilot, sx = (G == 2) ? (r >> 1) : r, g = (G == 2) ? (r & 1) : 0;
+              const float4 pv = __ldg(reinterpret_cast<const float4*>(pu + ((long long)i * ST + col0 + sx) * L + 2 * g));
+              float2 h0 = hbuf[2 * g * N + i], h1 = hbuf[(2 * g + 1) * N + i];
+              if (derot) {
+                h0 = cmul(h0, hsx[hh].rot_pos[sx]);
+                h1 = cmul(h1, hsx[hh].rot_pos[sx]);
+              }
+              const float2 e = cadd(cmul(make_float2(pv.x, pv.y), h0), cmul(make_float2(pv.z, pv.w), h1));
+              const float2 d = csub(ld_y(H, g, i, sx), cscale(e, beta));
+              noise_part += d.x * d.x + d.y * d.y;
+            }
+          } else
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             if (g < G) {
