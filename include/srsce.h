@@ -180,6 +180,17 @@ int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const i
 enum { SRSCE_FILL_IMPL_DIRECT = 0, SRSCE_FILL_IMPL_TENSOR = 1 };
 int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64_t n_units, int32_t impl, void* stream);
 
+/* EXTENSION (no counterpart in the reference, which takes the pilots as an input tensor,
+ * ce_rule_tensorized.py:746-747 -- parity unpinned): low-PAPR pilot sequences of TS 38.211 5.2.2 generated on the device
+ * in the estimator's pilot layout.
+ *   pilots  complex64 [n_ue][m_zc][n_dmrs][n_layers]: pilot n of UE b on every pilot symbol is rbar_{u,v}(n) for even
+ *           layers and e^{j pi n} rbar_{u,v}(n) for odd layers (cyclic shifts 0 and pi: the OCC-2 pair of a comb)
+ *   m_zc    sequence length = pilots per CDM group (30, or >= 36: Zadoff-Chu based with N_zc the largest prime < m_zc;
+ *           6 / 12 / 18 / 24 are table defined in the specification and not supported)
+ *   u_of    device int32 [n_ue]: sequence group u in 0..29;  v_of: device int32 [n_ue] base sequence number 0 / 1, or NULL */
+int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, int32_t n_layers, const int32_t* u_of,
+                     const int32_t* v_of, void* stream);
+
 /* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
 int srsce_last_launch_count(void);
 

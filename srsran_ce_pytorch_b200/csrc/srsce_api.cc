@@ -199,6 +199,23 @@ int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64
   }
 }
 
+int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, int32_t n_layers, const int32_t* u_of,
+                     const int32_t* v_of, void* stream) {
+  g_launches = 0;
+  if (n_ue < 0) return fail(SRSCE_ERR_INVALID, "negative UE count");
+  if (n_ue > 0 && (!pilots || !u_of)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if (n_dmrs < 1 || n_dmrs > SRSCE_MAX_SYMBOLS || n_layers < 1 || n_layers > SRSCE_MAX_LAYERS)
+    return fail(SRSCE_ERR_INVALID, "n_dmrs must be 1..14 and n_layers 1..4");
+  if (m_zc != 30 && m_zc < 36)
+    return fail(SRSCE_ERR_UNSUPPORTED, "sequence lengths 6, 12, 18, 24 are table defined in TS 38.211 5.2.2.2 (tables not included); supported: 30 and >= 36");
+  if (m_zc > SRSCE_TA_FFT) return fail(SRSCE_ERR_UNSUPPORTED, "sequence longer than 4096");
+  if (reinterpret_cast<uintptr_t>(pilots) & 7u) return fail(SRSCE_ERR_INVALID, "pilots must be 8-byte aligned");
+  std::string err;
+  const int rc = srsce::launch_gen_pilots(pilots, n_ue, m_zc, n_dmrs, n_layers, u_of, v_of, stream, err);
+  if (rc == SRSCE_OK && n_ue > 0) g_launches = 1;
+  return rc == SRSCE_OK ? rc : fail(rc, err);
+}
+
 int srsce_last_launch_count(void) { return g_launches; }
 
 }  // extern "C"

@@ -173,6 +173,11 @@ int max_dynamic_smem();
 int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
                        std::string& err);
 
+// srsce_seq.cu
+int launch_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, int32_t n_layers, const int32_t* u_of,
+                      const int32_t* v_of, void* stream, std::string& err);
+int largest_prime_below(int m);
+
 // srsce_fill_tc.cu
 int prepare_fill_tc(Plan& p, std::string& err);
 int launch_fill_tc(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
