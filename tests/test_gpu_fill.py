@@ -136,3 +136,53 @@ def test_config4_full_size_tensor_equals_direct(fill):
     for bb in range(2):
         mx, nmse = tol.grid_errors(b[bb].cpu().numpy(), want[bb])
         assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (bb, mx, nmse)
+
+
+def _fuzz_cases(n, seed):
+    import random
+    rnd = random.Random(seed)
+    out = []
+    while len(out) < n:
+        r = rnd.choice([1, 2, 3, 4, 5, 6, 7, 12])
+        layers = rnd.choice([1, 2, 3, 4])
+        cols = []
+        for _ in range((layers + 1) // 2):
+            pos = sorted(rnd.sample(range(12), r))
+            cols.append("".join("1" if k in pos else "0" for k in range(12)))
+        grid = rnd.choice([25, 52, 106, 273])
+        n_prb = min(rnd.choice([1, 2, 3, 7, 8, 9, 16, 17, 40, 100, 273]), grid)
+        start = rnd.randrange(0, grid - n_prb + 1)
+        s0 = rnd.choice([0, 0, 3])
+        n_alloc = rnd.choice([14 - s0, 14 - s0, max(1, 9 - s0)])
+        out.append((grid, start, n_prb, cols, layers, s0, n_alloc, rnd.choice([1, 7, 33, 65])))
+    return out
+
+
+FUZZ = _fuzz_cases(40, 4242)
+
+
+@pytest.mark.parametrize("k", range(len(FUZZ)))
+def test_fill_random_masks_match_oracle(k):
+    """Arbitrary 12-bit RE masks (irregular, R not dividing 12), band positions and widths that end tiles anywhere, odd
+    layer counts, partial allocations, unit counts that leave partial MMA batches: both implementations vs the oracle."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    grid, start, n, cols, L, s0, n_alloc, B = FUZZ[k]
+    hop1 = synth.make_hop(grid, start, n, [2], cols, (L + 1) // 2, 14, s0, n_alloc)
+    for fill in ("linear", "cnn"):
+        try:
+            plan = estimator.make_plan(grid, 14, L, hop1, synth.no_hop(), synth.make_config(30e3, "filter", True), fill)
+        except NotImplementedError:
+            continue                                          # (CNN operator rows wider than the kernel accepts: some irregular masks)
+        g = torch.Generator().manual_seed(100 + k)
+        h = torch.complex(torch.randn(B, 1, plan.info.n_re, L, generator=g), torch.randn(B, 1, plan.info.n_re, L, generator=g)).to(torch.complex64)
+        want = _expected(h[:2].numpy(), hop1, None, 12 * grid, 14, fill)
+        for impl in ("direct", "tensor"):
+            if impl == "tensor" and not plan.info.fill_tensor:
+                continue
+            out = plan.fill(h.cuda(), impl=impl)
+            for b in range(2):
+                mx, nmse = tol.grid_errors(out[b].cpu().numpy(), want[b])
+                assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (FUZZ[k], fill, impl, b, mx, nmse)
+            if B > 2:                                         # batch independence: the last unit equals a batch of its own
+                solo = plan.fill(h[-1:].cuda(), impl=impl)
+                assert torch.equal(solo[0], out[-1]), (FUZZ[k], fill, impl)
