@@ -180,7 +180,7 @@ def test_fill_random_masks_match_oracle(k):
             if impl == "tensor" and not plan.info.fill_tensor:
                 continue
             out = plan.fill(h.cuda(), impl=impl)
-            for b in range(2):
+            for b in range(min(2, B)):
                 mx, nmse = tol.grid_errors(out[b].cpu().numpy(), want[b])
                 assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (FUZZ[k], fill, impl, b, mx, nmse)
             if B > 2:                                         # batch independence: the last unit equals a batch of its own
