@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SRSCE_ABI_VERSION 2
+#define SRSCE_ABI_VERSION 3
 
 #define SRSCE_MAX_LAYERS 4
 #define SRSCE_MAX_SYMBOLS 14   /* the reference's CFO tables assume a 14-symbol slot (:809-820) */
@@ -190,6 +190,19 @@ int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64
  *   u_of    device int32 [n_ue]: sequence group u in 0..29;  v_of: device int32 [n_ue] base sequence number 0 / 1, or NULL */
 int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, int32_t n_layers, const int32_t* u_of,
                      const int32_t* v_of, void* stream);
+
+/* Host half of a host-buffer call (the reference's callers hold host arrays: scripts/validation/validate_all.py:367-382,
+ * :549-561).  The dense grid repeats one column over the allocated symbols (ce_rule_tensorized.py:346-347), so 13/14 of
+ * the bytes a device->host copy of it moves are copies; this call rebuilds the grid in HOST memory from the per-hop
+ * columns srsce_estimate_compact returned, on host threads, with non-temporal stores:
+ *   ch_sc      HOST complex64 [n_units][n_hops][n_sc][n_layers]  (srsce_estimate_compact's ch_sc, copied to the host)
+ *   ch_est     HOST complex64 [n_units][n_sc][n_sym][n_layers], fully overwritten -- bit-identical to what
+ *              srsce_estimate writes on the device for the same inputs
+ *   n_threads  host threads to use (<= 0: all the cores); a small persistent pool inside the library
+ * It performs NO arithmetic, only the copy: a plan whose grid carries the per-symbol CFO rotation (:922-929; cfo_defined
+ * and cfo_compensate) fails with SRSCE_ERR_UNSUPPORTED -- such plans take srsce_estimate and a dense device->host copy.
+ * Needs no CUDA device; blocking; may be called from several threads (calls are serialised on the pool). */
+int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads);
 
 /* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
 int srsce_last_launch_count(void);

@@ -13,7 +13,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SRSCE_LIBRARY", _HERE / "libsrsce.so"))   # override: A/B runs of two builds
 
 MAX_SYMBOLS = 14
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SMOOTH = {"none": 0, "mean": 1, "filter": 2}
 FILL_LINEAR, FILL_CNN = 0, 1
@@ -75,6 +75,8 @@ def _load() -> C.CDLL:
     lib.srsce_fill.restype = C.c_int
     lib.srsce_gen_pilots.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.srsce_gen_pilots.restype = C.c_int
+    lib.srsce_replicate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+    lib.srsce_replicate_host.restype = C.c_int
     lib.srsce_last_launch_count.restype = C.c_int
     if lib.srsce_abi_version() != ABI_VERSION:
         raise ImportError(f"libsrsce.so ABI {lib.srsce_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
@@ -84,7 +86,7 @@ def _load() -> C.CDLL:
 lib = _load()
 
 EXPORTS = ("srsce_abi_version", "srsce_last_error", "srsce_plan_create", "srsce_plan_destroy", "srsce_plan_query",
-           "srsce_plan_tables", "srsce_plan_fill_tensor_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed", "srsce_fill", "srsce_gen_pilots",
+           "srsce_plan_tables", "srsce_plan_fill_tensor_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed", "srsce_fill", "srsce_gen_pilots", "srsce_replicate_host",
            "srsce_last_launch_count")
 
 

@@ -216,6 +216,21 @@ int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, i
   return rc == SRSCE_OK ? rc : fail(rc, err);
 }
 
+int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads) {
+  if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
+  if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
+  if (n_units > 0 && (!ch_sc || !ch_est)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(ch_sc) & 7u) || (reinterpret_cast<uintptr_t>(ch_est) & 7u))
+    return fail(SRSCE_ERR_INVALID, "buffers must be 8-byte aligned");
+  try {
+    std::string err;
+    const int rc = srsce::replicate_host(plan->impl, ch_sc, ch_est, n_units, n_threads, err);
+    return rc == SRSCE_OK ? rc : fail(rc, err);
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
 int srsce_last_launch_count(void) { return g_launches; }
 
 }  // extern "C"

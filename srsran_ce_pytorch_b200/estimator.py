@@ -228,6 +228,28 @@ class Plan:
                                           C.c_void_p(stream)))
         return out
 
+    def replicate_host(self, ch: torch.Tensor, out: torch.Tensor, n_threads: int = 0) -> torch.Tensor:
+        """``srsce_replicate_host``: HOST tensors ch [B, n_hops, n_sc, L] (``estimate_compact``'s first output, copied
+        to the host) -> the dense [B, n_sc, n_sym, L] grid in ``out`` (host), written by the library's host threads.
+        A copy, no arithmetic: plans with a final CFO rotation raise NotImplementedError (use ``estimate``)."""
+        i = self.info
+        n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
+        for t in (ch, out):
+            if t.is_cuda or t.dtype != torch.complex64 or not t.is_contiguous() or t.is_conj() or t.is_neg():
+                raise ValueError("replicate_host takes contiguous complex64 host tensors")
+        n_units = int(ch.shape[0])
+        if tuple(ch.shape) != (n_units, n_hops, i.n_sc, i.n_layers):
+            raise IndexError(f"ch shape {tuple(ch.shape)} != [B, {n_hops}, {i.n_sc}, {i.n_layers}]")
+        if tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers):
+            raise IndexError(f"out shape {tuple(out.shape)} != [{n_units}, {i.n_sc}, {i.n_sym}, {i.n_layers}]")
+        _lib.raise_for(lib.srsce_replicate_host(self._h, ch.data_ptr(), out.data_ptr(), n_units, int(n_threads)))
+        return out
+
+    @property
+    def has_final_rotation(self) -> bool:
+        """The dense grid carries the per-symbol CFO rotation (:922-929): it cannot be rebuilt by replication alone."""
+        return bool(self.desc.cfo_compensate) and bool(self.info.cfo_defined)
+
     def expand_compact(self, ch: torch.Tensor, rot: torch.Tensor) -> torch.Tensor:
         """[B, n_hops, n_sc, L] x [B, n_sym] -> the dense [B, n_sc, n_sym, L] grid of the reference contract
         (plain torch ops; for consumers and tests -- the fused dense path is ``estimate``)."""

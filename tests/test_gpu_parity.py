@@ -324,6 +324,47 @@ def test_host_pipeline_matches_device_path():
     assert torch.equal(hc[0], ch.cpu()) and torch.equal(hc[1], rot.cpu()) and torch.equal(h_sc, sc.cpu())
 
 
+@pytest.mark.parametrize("two_hops", [False, True], ids=["1hop", "2hop"])
+def test_host_pipeline_with_host_side_replication(two_hops):
+    """HostPipeline(replicate="host"): the per-hop columns cross PCIe and srsce_replicate_host rebuilds the dense grid
+    in the caller's host buffer -- bit-identical to the grid the fused kernel writes on the device (the host side only
+    copies); the scalars agree to float32 summation order (the compact launch may use another CTA shape).  Plans with
+    a final CFO rotation are refused ("auto" falls back to the dense device->host copy for them)."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    from srsran_ce_pytorch_b200.hostio import HostPipeline, srs_channel_estimator_host
+    if two_hops:
+        hop1 = synth.make_hop(52, 2, 24, [2], "comb2", 2, start_symbol=0, n_alloc=7)
+        hop2 = synth.make_hop(52, 20, 24, [9], "comb2", 2, start_symbol=7, n_alloc=7)
+        cfg = synth.make_config(30e3, "filter", True)
+        data = synth.make_units(hop1, hop2, cfg, 4, 40, pilot_share=4, seed=3, device="cuda")
+        plan = estimator.make_plan(52, 14, 4, hop1, hop2, cfg)
+    else:
+        hop1, hop2, cfg, data = _config2(40, syms=(13,))
+        plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    assert not plan.has_final_rotation
+    dense, sc = plan.estimate(data["rx"], data["pilots"], 1.0, 4)
+    h_rx, h_pil = data["rx"].cpu().pin_memory(), data["pilots"].cpu().pin_memory()
+    h_out = torch.full(dense.shape, float("nan"), dtype=torch.complex64).pin_memory()
+    h_sc = torch.empty(sc.shape, dtype=torch.float64).pin_memory()
+    for streams in (2, 3):
+        pipe = HostPipeline(plan, 16, 4, n_streams=streams, replicate="host")
+        h_out.fill_(float("nan"))
+        pipe.run(h_rx, h_pil, 1.0, h_out, h_sc)
+        assert torch.equal(torch.view_as_real(h_out), torch.view_as_real(dense.cpu()))
+        assert torch.allclose(h_sc, sc.cpu(), rtol=2e-6, atol=1e-12)
+        assert torch.equal(h_sc[:, 3], sc.cpu()[:, 3])                          # time alignment: exact index
+        assert pipe.launches == 3 and pipe.d2h_bytes == 40 * plan.info.n_sc * 4 * 8 * (2 if two_hops else 1) + 40 * 48
+    out2, sc2 = srs_channel_estimator_host(plan, h_rx, h_pil, 1.0, 4, chunk_units=16)      # "auto" picks the host side here
+    assert torch.equal(torch.view_as_real(out2), torch.view_as_real(dense.cpu())) and torch.allclose(sc2, sc.cpu(), rtol=2e-6, atol=1e-12)
+    # a plan with the final rotation: host replication refused, "auto" takes the dense copy
+    hop1r, hop2r, cfgr, datar = _config2(8, syms=(3, 10))
+    planr = estimator.make_plan(273, 14, 4, hop1r, hop2r, cfgr)
+    assert planr.has_final_rotation
+    with pytest.raises(NotImplementedError):
+        HostPipeline(planr, 8, 4, replicate="host")
+    assert HostPipeline(planr, 8, 4, replicate="auto").replicate == "device"
+
+
 @pytest.mark.parametrize("syms", [(13,), (3, 10)], ids=["single-cta", "cta-pair"])
 def test_unit_counts_around_the_resident_cta_count(syms):
     """Launches of 1 ... 2 x SMs + 1 units: grids smaller than, equal to and just above the number of resident CTAs

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(_lib.lib, name), name
-    assert _lib.lib.srsce_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib.srsce_abi_version() == _lib.ABI_VERSION == 3
 
 
 def _plan(pattern, n_prbs, n_layers, smoothing="filter", fill="linear", grid=52, syms=(2, 11), start=3, **kw):
