@@ -11,7 +11,8 @@
  *
  * Ownership / threading contract
  *   - The caller owns every device buffer passed to srsce_estimate / srsce_estimate_compact and keeps it
- *     alive until the stream reaches the kernel.  The library allocates nothing per call, never
+ *     alive until the stream reaches the kernel.  The library allocates nothing per call (one exception: plans with
+ *     srsce_plan_info.h_in_global take a stream-ordered scratch from the device's memory pool per launch), never
  *     synchronises and never touches the default stream unless it is the stream passed in.
  *   - A plan owns its (small) host tables and their device copies; it is immutable after creation
  *     and may be shared by threads and streams.  A plan is bound to the CUDA device that was
@@ -42,7 +43,7 @@ enum {
   SRSCE_OK = 0,
   SRSCE_ERR_INVALID = -1,     /* ValueError in the reference (unknown smoothing :668, CP vector < 14 :815, ...) */
   SRSCE_ERR_ASSERT = -2,      /* AssertionError in the reference (hop overlap :862, differing RE masks :869) */
-  SRSCE_ERR_UNSUPPORTED = -3, /* geometry outside what one CTA can hold */
+  SRSCE_ERR_UNSUPPORTED = -3, /* outside the documented limits (n_sc <= 4096, <= 4 layers, <= 14 symbols) */
   SRSCE_ERR_NO_DEVICE = -4,
   SRSCE_ERR_CUDA = -5
 };
@@ -101,6 +102,9 @@ typedef struct srsce_plan_info {
   int32_t fill_tensor_tiles;  /* 96-row tiles of the hop band */
   int32_t fill_tensor_kinds;  /* distinct operator tiles (first / interior / last ...) kept in shared memory */
   int32_t fill_tensor_a_terms;/* bf16 terms per operator coefficient (1 when the coefficients are exact in bf16) */
+  int32_t h_in_global;        /* 1: the smoothed pilots of a unit do not fit in shared memory beside the rest and live in a
+                               * per-CTA global scratch (largest two-hop geometries; compute calls then make one
+                               * stream-ordered allocation per launch, cudaMallocAsync / cudaFreeAsync on the caller's stream) */
 } srsce_plan_info;
 
 int srsce_abi_version(void);

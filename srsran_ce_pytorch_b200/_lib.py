@@ -41,7 +41,8 @@ class PlanInfo(C.Structure):
                 ("smem_bytes", C.c_int32), ("threads", C.c_int32), ("fill_terms", C.c_int32),
                 ("has_device", C.c_int32), ("bytes_per_unit", C.c_int64), ("fill_tensor", C.c_int32),
                 ("fill_tensor_k", C.c_int32), ("fill_tensor_terms", C.c_int32), ("fill_tensor_units", C.c_int32),
-                ("fill_tensor_tiles", C.c_int32), ("fill_tensor_kinds", C.c_int32), ("fill_tensor_a_terms", C.c_int32)]
+                ("fill_tensor_tiles", C.c_int32), ("fill_tensor_kinds", C.c_int32), ("fill_tensor_a_terms", C.c_int32),
+                ("h_in_global", C.c_int32)]
 
 
 def _load() -> C.CDLL:

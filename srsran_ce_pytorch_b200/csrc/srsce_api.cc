@@ -77,6 +77,7 @@ int srsce_plan_query(const srsce_plan* plan, srsce_plan_info* info) {
   info->fill_tensor_k = plan->impl.fill_tc.k_tile;
   info->fill_tensor_terms = plan->impl.fill_tc.n_prod;
   info->fill_tensor_units = plan->impl.fill_tc.units;
+  info->h_in_global = v.h_global;
   info->fill_tensor_tiles = plan->impl.fill_tc.n_tiles;
   info->fill_tensor_kinds = plan->impl.fill_tc.n_kinds;
   info->fill_tensor_a_terms = plan->impl.fill_tc.n_a;

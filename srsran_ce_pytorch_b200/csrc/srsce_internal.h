@@ -78,6 +78,7 @@ struct PlanDev {
   int32_t hall_bufs;       // 1: writers and the next unit's FIR alternate on one pilot buffer; 2: double buffered
   int32_t y_bufs;          // staging buffers of the received pilot REs: 2 = fetched a whole unit ahead, 1 = during the IFFT
   int32_t fir_per_group;   // FIR input (ext) holds one CDM group (<= 2 layers) at a time instead of all layers
+  int32_t h_global;        // 1: the smoothed pilots live in a per-CTA global scratch, not in shared memory (layout F)
   int32_t ta_radix4;       // time-alignment transform: 1 = radix-4 passes + twiddle table (light phase A), 0 = register-blocked radix 8
   // shared-memory carve-up (byte offsets from the dynamic smem base)
   int32_t off_h, off_y, off_ext, off_tile, off_misc, smem_bytes, ext_elems;

@@ -99,6 +99,7 @@ __device__ long long* g_prof_buf = nullptr;       // [gridDim.x][kProfSlots] cyc
 // Named barriers: 0 is __syncthreads (whole CTA); 1 joins the estimator warps only; 2 ("full") hands
 // hall[b] + store-slot table b from the estimator warps to the writer warps, 4+b ("empty") hands them back.
 constexpr int kBarA = 1, kBarFull = 2, kBarEmpty = 4;   // + buffer index (0/1)
+constexpr int kModeUnstaged = 0, kModeStaged = 1, kModeGlobalH = 2;   // estimate_kernel's MODE
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 template <int NA>
@@ -370,13 +371,17 @@ __device__ __forceinline__ void stream_full_tile_2hop(const float4* __restrict__
 //   ext[layer][EF]             raw pilots with nv virtual pilots and `pad` zeros either side (FIR input),
 //                              EF = N + 2*nv + 2*pad; later the FFT scratch
 //   tiles[writer warp][hop][32][L]  interpolated rows being streamed out
-template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT, bool STAGED>
+template <int NA, int VEC, bool TWO_HOPS, bool HAS_ROT, int MODE>
 __global__ void __launch_bounds__(cta_threads(NA, TWO_HOPS), NA == 256 ? 2 : 1)
 estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx, long long su, long long ssc,
                 long long ssym, const float2* __restrict__ pilots, int pilot_share, double beta_d,
                 float2* __restrict__ out, double* __restrict__ scalars, long long n_units, int dbg_arg,
                 float2* __restrict__ out_c, float2* __restrict__ rot_c, const long long* __restrict__ rx_index,
-                const float2* __restrict__ h_in) {
+                const float2* __restrict__ h_in, float2* h_scratch) {
+  // MODE 1: the received pilot REs are staged in shared memory; 0: read where they are used (staging buffer does not
+  // fit); 2: as 0, and the smoothed pilots live in a per-CTA global scratch (L2 resident) instead of shared memory --
+  // the largest two-hop geometries (dense mask on two full-band hops), where 2 * N * L * 8 bytes alone fill the SM
+  constexpr bool STAGED = MODE == kModeStaged, H_GLOBAL = MODE == kModeGlobalH;
 #ifdef SRSCE_PROFILING
   const int dbg = dbg_arg;                                  // ablation bits (profiling build only)
 #else
@@ -386,7 +391,8 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
   constexpr int kWarpsB = (NA == 256) ? (TWO_HOPS ? 6 : 4) : (TWO_HOPS ? 8 : 6);   // = writer_warps(NA, TWO_HOPS)
   constexpr int kCtaThreads = NA + 32 * kWarpsB;
   extern __shared__ __align__(16) unsigned char smem[];
-  float2* const hall0 = reinterpret_cast<float2*>(smem + P.off_h);     // hall_bufs buffers of n_hops*L*N
+  float2* const hall0 = H_GLOBAL ? h_scratch + (long long)blockIdx.x * (P.hall_bufs * (TWO_HOPS ? 2 : 1) * P.n_layers * P.n_re)
+                                 : reinterpret_cast<float2*>(smem + P.off_h);   // hall_bufs buffers of n_hops*L*N
   float2* const ystage = reinterpret_cast<float2*>(smem + P.off_y);
   float2* const tiles = reinterpret_cast<float2*>(smem + P.off_tile);
   float2* const ext = reinterpret_cast<float2*>(smem + P.off_ext);
@@ -1213,9 +1219,10 @@ estimate_kernel(const __grid_constant__ PlanDev P, const float2* __restrict__ rx
 }
 
 typedef void (*KernelFn)(const PlanDev, const float2*, long long, long long, long long, const float2*, int,
-                         double, float2*, double*, long long, int, float2*, float2*, const long long*, const float2*);
+                         double, float2*, double*, long long, int, float2*, float2*, const long long*, const float2*,
+                         float2*);
 
-template <int NA, bool STAGED>
+template <int NA, int STAGED>
 KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
   if (vec == 2) {
     if (two_hops) return has_rot ? estimate_kernel<NA, 2, true, true, STAGED> : estimate_kernel<NA, 2, true, false, STAGED>;
@@ -1227,8 +1234,12 @@ KernelFn pick_kernel_na(int vec, bool two_hops, bool has_rot) {
 
 KernelFn pick_kernel(const PlanDev& v, bool fill_only = false) {
   const bool rot = v.cfo_compensate && v.cfo_defined && !fill_only, two = v.n_hops == 2;   // (the fill has no CFO rotation)
-  if (v.y_bufs == 0) return pick_kernel_na<512, false>(v.vec, two, rot);    // the planner pairs the unstaged layout with NA = 512
-  return v.est_threads == 512 ? pick_kernel_na<512, true>(v.vec, two, rot) : pick_kernel_na<256, true>(v.vec, two, rot);
+  if (v.h_global) {                                                            // two-hop plans only (srsce_plan.cc, layout F)
+    if (v.vec == 2) return rot ? estimate_kernel<512, 2, true, true, kModeGlobalH> : estimate_kernel<512, 2, true, false, kModeGlobalH>;
+    return rot ? estimate_kernel<512, 1, true, true, kModeGlobalH> : estimate_kernel<512, 1, true, false, kModeGlobalH>;
+  }
+  if (v.y_bufs == 0) return pick_kernel_na<512, kModeUnstaged>(v.vec, two, rot);    // the planner pairs the unstaged layout with NA = 512
+  return v.est_threads == 512 ? pick_kernel_na<512, kModeStaged>(v.vec, two, rot) : pick_kernel_na<256, kModeStaged>(v.vec, two, rot);
 }
 
 // Ablation switch, PROFILING BUILD ONLY (SRSCE_DEBUG_ABLATE: bit 0 skips phase A, bit 1 skips phase B, bit 2 skips
@@ -1346,6 +1357,19 @@ void release_plan(Plan& p) {
   p.d_twiddle = p.d_fill_idx = p.d_fill_coef = p.d_fill_tc_a = nullptr;
 }
 
+// Plans of layout F keep the smoothed pilots of each resident CTA in global memory: a stream-ordered allocation per
+// launch (the plan stays immutable and shareable between streams; the pool serves repeat calls without a driver call).
+static int alloc_h_scratch(const PlanDev& v, unsigned grid, void* stream, float2** out, std::string& err) {
+  *out = nullptr;
+  if (!v.h_global) return SRSCE_OK;
+  const size_t bytes = size_t(grid) * v.hall_bufs * v.n_hops * v.n_layers * v.n_re * sizeof(float2);
+  void* ptr = nullptr;
+  const cudaError_t e = cudaMallocAsync(&ptr, bytes, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { err = cuda_msg("cudaMallocAsync(smoothed-pilot scratch)", e); return SRSCE_ERR_CUDA; }
+  *out = static_cast<float2*>(ptr);
+  return SRSCE_OK;
+}
+
 int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], const void* pilots, int pilot_share,
                     double beta, void* out, double* scalars, int64_t n_units, void* stream, int* launches,
                     std::string& err, void* out_compact, void* rot_compact, const int64_t* rx_index) {
@@ -1363,12 +1387,15 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
   KernelFn fn = pick_kernel(v);
   const long long cap = (long long)p.n_sms * (pair ? p.ctas_per_sm_pair : p.ctas_per_sm);
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
+  float2* h_scratch = nullptr;
+  if (int rc = alloc_h_scratch(v, grid, stream, &h_scratch, err)) return rc;
   fn<<<grid, cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       v, static_cast<const float2*>(rx), (long long)strides[0], (long long)strides[1], (long long)strides[2],
       static_cast<const float2*>(pilots), pilot_share, beta, static_cast<float2*>(out), scalars, (long long)n_units,
       debug_mode(), static_cast<float2*>(out_compact), static_cast<float2*>(rot_compact),
-      reinterpret_cast<const long long*>(rx_index), nullptr);
+      reinterpret_cast<const long long*>(rx_index), nullptr, h_scratch);
   cudaError_t e = cudaGetLastError();
+  if (h_scratch) cudaFreeAsync(h_scratch, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { err = cuda_msg("kernel launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;
   return SRSCE_OK;
@@ -1388,10 +1415,13 @@ int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n
   KernelFn fn = pick_kernel(v, true);
   const long long cap = (long long)p.n_sms * (pair ? p.ctas_per_sm_pair : p.ctas_per_sm);
   const unsigned grid = unsigned(n_units < cap ? n_units : cap);
+  float2* h_scratch = nullptr;
+  if (int rc = alloc_h_scratch(v, grid, stream, &h_scratch, err)) return rc;
   fn<<<grid, cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
       v, nullptr, 0, 0, 0, nullptr, 1, 1.0, static_cast<float2*>(out), nullptr, (long long)n_units, 0, nullptr, nullptr,
-      nullptr, static_cast<const float2*>(h_pilots));
+      nullptr, static_cast<const float2*>(h_pilots), h_scratch);
   cudaError_t e = cudaGetLastError();
+  if (h_scratch) cudaFreeAsync(h_scratch, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { err = cuda_msg("fill launch", e); return SRSCE_ERR_CUDA; }
   *launches = 1;
   return SRSCE_OK;

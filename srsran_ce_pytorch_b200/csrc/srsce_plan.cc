@@ -599,10 +599,11 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
   //      stretch between "writers done" and "next FIR done" is shortest when both CDM groups are de-spread ahead).
   //   D  the same with the slim footprint (the largest geometries).
   //   E  D without a staging buffer: the pilot REs are read from the received grid where they are used (dense
-  //      masks with several pilot symbols).  What does NOT fit even so: two-hop plans whose smoothed pilots of both
-  //      hops (2 * N * L * 8 bytes) leave no room for the rest -- in practice the dense mask (12 pilots per PRB) on
-  //      two hops at 273 PRB with >= 3 layers or 341 PRB with >= 2 layers (host sweep of 1 120 geometries: those 20
-  //      and nothing else).  They fail with SRSCE_ERR_UNSUPPORTED; DESIGN.md section 1 lists the envelope.
+  //      masks with several pilot symbols).
+  //   F  E with the smoothed pilots in a per-CTA global scratch (L2 resident) instead of shared memory: two-hop plans
+  //      whose smoothed pilots of both hops (2 * N * L * 8 bytes) leave no room for the rest -- in practice the dense
+  //      mask (12 pilots per PRB) on two hops at 273 PRB with >= 3 layers or 341 PRB with >= 2 layers (host sweep of
+  //      1 120 geometries: those 20 and nothing else).  Slower (every pass over the pilots goes to L2) but complete.
   //   Measured on B200 (comb-2, 273 PRB): single staging buffer 0.60 (C) / 0.59 (D), two staging buffers 0.58 / 0.57,
   //   smoothed pilots double buffered 0.50-0.54 of the HBM peak -- phase A re-reads the pilots through L1, the
   //   gather of the next unit pollutes L1 unless it is issued after the noise estimate, and L1 is what shared
@@ -613,7 +614,8 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     const int fir_len = N + 2 * v.n_virtual + 2 * (v.n_taps / 2);
     const int fft_default = std::max(1, std::min(L, 4096 / v.fft_size));
     auto up16 = [](int bytes) { return ((bytes + 15) / 16) * 16; };
-    auto layout = [&](int na, int hall_bufs, int y_bufs, bool slim) {
+    auto layout = [&](int na, int hall_bufs, int y_bufs, bool slim, bool h_global = false) {
+      v.h_global = h_global ? 1 : 0;
       const int ext_layers = slim ? std::min(L, 2) : L;
       v.fir_per_group = (slim && L > 2) ? 1 : 0;
       v.fft_layers = slim ? std::min(fft_default, 2) : fft_default;
@@ -626,7 +628,7 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
       v.hall_bufs = hall_bufs;
       v.y_bufs = y_bufs;
       v.off_h = 0;
-      v.off_y = v.off_h + up16(hall_bufs * h_elems * 8);
+      v.off_y = v.off_h + (h_global ? 0 : up16(hall_bufs * h_elems * 8));
       v.off_ext = v.off_y + up16(y_bufs * y_unit * 8);
       v.off_tile = v.off_ext + up16(ext * 8);
       v.off_misc = v.off_tile + up16(tile_elems * 8);
@@ -650,8 +652,9 @@ int build_plan(const srsce_plan_desc& d, Plan& p, std::string& err) {
     v.ta_radix4 = (light && G == 2 && v.fft_size == 1024 && d.fill == SRSCE_FILL_LINEAR) ? 1 : 0;
     if (!(light && layout(512, 1, 1, false) <= one_cta_l1_budget) &&
         layout(256, 1, 2, false) > two_cta_budget && layout(256, 1, 1, true) > two_cta_budget &&
-        layout(512, 1, 1, false) > 227 * 1024 && layout(512, 1, 1, true) > 227 * 1024)
-      layout(512, 1, 0, true);
+        layout(512, 1, 1, false) > 227 * 1024 && layout(512, 1, 1, true) > 227 * 1024) {
+      if (layout(512, 1, 0, true) > 227 * 1024 && n_hops == 2) layout(512, 1, 0, true, true);   // E, else F
+    }
     // A plan that runs the single CTA also keeps the CTA-pair layout: without the scattered gather (received grids
     // shared by the UEs of a slot, symbol-major grids) or without the dense write (compact output) the pair is the
     // faster shape (same box: shared grids 0.948 vs 0.885, compact output 28.9 vs 25.2 M estimates/s).

@@ -101,6 +101,61 @@ def test_batched_units_match_oracle(case, fill):
         tol.check_scalars(got, want[1:], float(cfg.scs), diag["ta_margin"], tag=f"{case}/{fill}/{b}")
 
 
+GLOBAL_H_CASES = [
+    # grid PRBs, layers, hop-1 pilot symbols, hop-2 pilot symbols, smoothing, cfo compensation, fill
+    (273, 4, [3], [10], "filter", True, "linear"),
+    (273, 3, [2, 4], [9, 11], "filter", True, "linear"),       # CFO estimated and compensated: final rotation
+    (341, 2, [3], [10], "mean", True, "linear"),
+    (341, 4, [2, 4], [9, 11], "filter", False, "linear"),
+    (341, 3, [3], [10], "none", True, "cnn"),
+]
+
+
+@pytest.mark.parametrize("case", GLOBAL_H_CASES, ids=[f"g{i}" for i in range(len(GLOBAL_H_CASES))])
+def test_largest_two_hop_geometries_run_with_the_smoothed_pilots_in_global_memory(case):
+    """The dense mask on two full-band hops: the smoothed pilots of both hops do not fit in shared memory, the planner
+    keeps them in a per-CTA global scratch (``info.h_in_global``).  Same parity bar as every other geometry, for more
+    units than there are resident CTAs (the scratch is reused across the units of a CTA), plus the fill seam."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    grid, L, syms1, syms2, sm, cfo, fill = case
+    hop1 = synth.make_hop(grid, 0, grid, syms1, "dense", (L + 1) // 2, start_symbol=0, n_alloc=7)
+    hop2 = synth.make_hop(grid, 0, grid, syms2, "dense", (L + 1) // 2, start_symbol=7, n_alloc=7)
+    cfg = synth.make_config(30e3, sm, cfo)
+    plan = estimator.make_plan(grid, 14, L, hop1, hop2, cfg, fill)
+    assert plan.info.h_in_global == 1
+    n_units = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 3
+    # (mean smoothing: a nearly flat channel -- over 4 092 pilots of the default 100-sample delay spread the band mean
+    #  cancels to ~1 % of its terms and float32 summation order alone moves it by 1e-5, see tests/tolerances.py)
+    data = synth.make_units(hop1, hop2, cfg, L, n_units, seed=5, device="cuda", max_delay=1.0 if sm == "mean" else 100.0)
+    out, sc = plan.estimate(data["rx"], data["pilots"], 1.0, 1)
+    again, sc_again = plan.estimate(data["rx"][-4:], data["pilots"][-4:], 1.0, 1)
+    assert torch.equal(again, out[-4:]) and torch.equal(sc_again, sc[-4:])
+    rx, pil = data["rx"].cpu().numpy(), data["pilots"].cpu().numpy()
+    o, s = out.cpu().numpy(), sc.cpu().numpy()
+    for b in (0, n_units // 2, n_units - 1):
+        diag = {}
+        want = ce_oracle.estimate(rx[b], pil[b], 1.0, hop1, hop2, cfg, fill="cnn" if fill == "cnn" else "tensorized",
+                                  diagnostics=diag)
+        mx, nmse = tol.grid_errors(o[b], want[0])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.grid_nmse_gate([syms1, syms2], cfo, sm), (case, b, mx, nmse)
+        got = [s[b, 0], s[b, 1], s[b, 2], s[b, 3], s[b, 4] if s[b, 5] else None]
+        tol.check_scalars(got, want[1:], float(cfg.scs), diag["ta_margin"], tag=f"{case}/{b}")
+    # compact output of the same plan rebuilds the dense grid
+    ch, rot, sc2 = plan.estimate_compact(data["rx"][:8], data["pilots"][:8], 1.0, 1)
+    mx, nmse = tol.grid_errors(plan.expand_compact(ch, rot).cpu().numpy(), o[:8])
+    assert mx <= 1e-6 and nmse <= 1e-13 and torch.equal(sc2, sc[:8]), (mx, nmse)
+    # the fill seam of the same plan (direct implementation; smoothed pilots in, no final rotation)
+    i = plan.info
+    g = torch.Generator(device="cuda").manual_seed(1)
+    h = torch.view_as_complex(torch.randn((5, 2, i.n_re, L, 2), device="cuda", generator=g))
+    filled = plan.fill(h, impl="direct")
+    from tests.test_gpu_fill import _expected
+    want = _expected(h[:2].cpu().numpy(), hop1, hop2, i.n_sc, 14, fill)
+    mx, nmse = tol.grid_errors(filled[:2].cpu().numpy(), want)
+    assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (mx, nmse)
+    assert torch.isfinite(torch.view_as_real(filled)).all()
+
+
 def _config2(n_units, syms=(13,), seed=1234, share=4):
     from srsran_ce_pytorch_b200 import synth
     hop1 = synth.make_hop(273, 0, 273, list(syms), "comb4", 2)

@@ -191,20 +191,20 @@ def test_tensor_fill_is_refused_where_it_does_not_apply():
         plan.fill_tensor_tables()
 
 
-def test_unsupported_envelope_is_exactly_the_documented_one():
-    """the only geometries (n_sc <= 4096, <= 4 layers, <= 14 symbols) the fused kernel refuses are
-    two-hop plans whose smoothed pilots of both hops do not fit in shared memory -- the dense mask at 273 PRB with
-    >= 3 layers and at 341 PRB with >= 2 layers.  Everything else in this sweep must plan."""
-    refused = set()
+def test_every_geometry_inside_the_limits_plans_and_the_global_scratch_envelope_is_the_documented_one():
+    """inside n_sc <= 4096, <= 4 layers, <= 14 symbols every geometry plans.  The only plans whose
+    smoothed pilots do not fit in shared memory (and live in a per-CTA global scratch: ``info.h_in_global``) are two-hop
+    plans with the dense mask at 273 PRB with >= 3 layers and at 341 PRB with >= 2 layers."""
+    in_global = set()
     for grid in (106, 273, 341):
         for pat in ("comb2", "comb4", "type2", "comb6", "dense"):
             for n_layers in (1, 2, 3, 4):
                 for syms, syms2 in (([13], None), ([2, 5, 8, 11], None), ([3], [10]), ([2, 4], [9, 11])):
                     hop1 = synth.make_hop(grid, 0, grid, syms, pat, (n_layers + 1) // 2)
                     hop2 = synth.make_hop(grid, 0, grid, syms2, pat, (n_layers + 1) // 2) if syms2 else synth.no_hop()
-                    try:
-                        estimator.make_plan(grid, 14, n_layers, hop1, hop2, synth.make_config(30e3, "filter", True))
-                    except NotImplementedError:
-                        refused.add((grid, pat, n_layers, syms2 is not None))
+                    plan = estimator.make_plan(grid, 14, n_layers, hop1, hop2, synth.make_config(30e3, "filter", True))
+                    assert plan.info.smem_bytes <= 227 * 1024
+                    if plan.info.h_in_global:
+                        in_global.add((grid, pat, n_layers, syms2 is not None))
     want = {(273, "dense", 3, True), (273, "dense", 4, True), (341, "dense", 2, True), (341, "dense", 3, True), (341, "dense", 4, True)}
-    assert refused == want, refused ^ want
+    assert in_global == want, in_global ^ want

@@ -27,7 +27,12 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_
     if smoothing == "mean":
         # the whole band collapses to the float32 mean of N pilots whose phases rotate across the band: the mean can
         # be ~10x smaller than its terms, and numpy's pairwise sum vs the kernel's per-thread partial sums then differ
-        # by ~1e-6 of it (1 of 1200 random geometries: constant error 9e-8 on a layer of mean magnitude 0.05)
+        # by ~1e-6 of it (1 of 1200 random geometries: constant error 9e-8 on a layer of mean magnitude 0.05).
+        # This gate holds for the campaign's sizes (<= 106 PRB).  It is a conditioning rule, not a constant: on the
+        # synthetic 100-sample delay spread the mean of >= 3 276 pilots (dense mask at 273 / 341 PRB) cancels to ~1 % of
+        # its terms and kernel vs oracle reach NMSE 8e-11 / 4e-10 on every layout (tools/mean_probe.py) -- the kernel
+        # sums float32 partials of 8 terms and then float64, numpy sums pairwise in float32, torch in its own order.
+        # Tests of mean smoothing at those sizes use a nearly flat channel (max_delay = 1).
         gate = 10.0 * GRID_NMSE
     if smoothing == "filter" and n_pilots is not None and n_pilots <= 12:
         # every output sits next to the virtual pilots, which extrapolate float32 `angle` values (CUDA atan2f: <= 2 ulp,
