@@ -430,7 +430,7 @@ def run_ours(args):
             "dtype": "complex64 (f32) data, f64 scalars", "data": "synthetic",
             "config": workload_config(args.slots, e2e_slots),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "estimate_kernel<%d,2,false,false,true>" % (512 if plan.info.threads > 512 else 256), "kernel_ms": kern_ms,
+                         "traffic": traffic, "kernel": "estimate_kernel<%d,2,false,false,1>" % (512 if plan.info.threads > 512 else 256), "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_unit": bpu, "units_per_launch": n_local, "peak_source": peak_src},
             "e2e": {"value": LAYERS * n_e2e * world * e2e_steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
