@@ -1,7 +1,7 @@
 """Drop-in for /root/reference src/ce_dl_cnn.py (entry point :802): the estimator whose
 frequency interpolation is the fixed-stencil partial-convolution inpainting (:433-508) and whose
 smoothed pilots may be blended with a low-pass copy (``CNNSmoothingAlpha``, :712-717, :864-867)."""
-from srsran_ce_pytorch_b200.estimator import srs_channel_estimator as _estimate
+from srsran_ce_pytorch_b200.estimator import srs_channel_estimator_any as _estimate
 from srsran_ce_pytorch_b200.types import CnnEstimatorConfig, EstimatorConfig, HopConfig
 
 __all__ = ["HopConfig", "EstimatorConfig", "CnnEstimatorConfig", "srs_channel_estimator"]

@@ -1,7 +1,7 @@
 """Drop-in for /root/reference src/ce_rule_baseline.py (entry point :761).  The baseline and the
 tensorized reference compute the same estimator (they differ by <= 3.3e-7 relative),
 so both names are served by the same fused kernel."""
-from srsran_ce_pytorch_b200.estimator import srs_channel_estimator as _estimate
+from srsran_ce_pytorch_b200.estimator import srs_channel_estimator_any as _estimate
 from srsran_ce_pytorch_b200.types import EstimatorConfig, HopConfig
 
 __all__ = ["HopConfig", "EstimatorConfig", "srs_channel_estimator"]

@@ -426,6 +426,24 @@ def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *,
     return grid[0], sc[0, 0], sc[0, 1], sc[0, 2], sc[0, 3], cfo
 
 
+def srs_channel_estimator_any(received_rg, pilots, beta_dmrs, hop1, hop2, config, *, fill: str = "linear"):
+    """``srs_channel_estimator`` for callers that hold HOST arrays, as every caller of the reference does
+    (scripts/validation/validate_all.py:367-382, :543): CPU tensors (or numpy arrays) are copied to the current CUDA
+    device, the estimate runs there, and the six results come back as CPU tensors -- so the reference's scripts run
+    unmodified on top of ``compat/``.  CUDA tensors go straight through.  This is a transfer, not a fallback: without
+    a CUDA device it raises, there is no CPU compute path."""
+    rx = torch.as_tensor(received_rg)
+    if rx.is_cuda:
+        return srs_channel_estimator(rx, pilots, beta_dmrs, hop1, hop2, config, fill=fill)
+    if not torch.cuda.is_available():
+        raise RuntimeError("srsran_ce_pytorch_b200 needs a CUDA device (sm_100a): host arrays are copied to it and back, "
+                           "there is no CPU compute path")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = srs_channel_estimator(_as_c64(rx).to(dev), _as_c64(torch.as_tensor(pilots)).to(dev), beta_dmrs, hop1, hop2,
+                                config, fill=fill)
+    return tuple(t.cpu() for t in out)
+
+
 def unpack_scalars(scalars: torch.Tensor) -> dict:
     return {name: scalars[:, k] for k, name in enumerate(_SCALAR_FIELDS)}
 

@@ -9,7 +9,11 @@ import torch
 
 from oracle import ce_oracle
 from tests import tolerances as tol
+from pathlib import Path
+
 from tests.golden_io import case_names, load_case
+
+ROOT = Path(__file__).resolve().parents[1]
 
 pytestmark = pytest.mark.gpu
 NAMES = case_names()
@@ -46,6 +50,38 @@ def test_rule_estimator_matches_reference(name):
         assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (name, variant, mx, nmse)
         tol.check_scalars(_scalars(out), c["ref"][f"{variant}_scalars"], float(c["cfg"].scs), margin,
                           tag=f"{name}/{variant}")
+
+
+def test_zero_code_switch_with_host_arrays():
+    """with compat/ ahead of the reference's src/ on sys.path, ``from ce_rule_tensorized import
+    ...`` serves the reference's own call shape -- HOST tensors (or numpy arrays) in, CPU tensors out, as
+    scripts/validation/validate_all.py:367-382 / :543 / :549-561 use it -- with the arithmetic on the GPU."""
+    import importlib
+    import sys
+    compat_dir = str(ROOT / "srsran_ce_pytorch_b200" / "compat")
+    sys.path.insert(0, compat_dir)
+    try:
+        mods = [importlib.import_module(n) for n in ("ce_rule_tensorized", "ce_rule_baseline", "ce_dl_cnn")]
+    finally:
+        sys.path.remove(compat_dir)
+        for n in ("ce_rule_tensorized", "ce_rule_baseline", "ce_dl_cnn"):
+            sys.modules.pop(n, None)
+    c = load_case(NAMES[0])
+    for mod, variant in zip(mods, ("tensorized", "baseline", "cnn")):
+        if f"{variant}_grid" not in c["ref"]:
+            continue
+        assert {"HopConfig", "EstimatorConfig", "srs_channel_estimator"} <= set(dir(mod))
+        rx, pil = torch.as_tensor(c["rx"]).cpu(), torch.as_tensor(c["pilots"]).cpu()
+        out = mod.srs_channel_estimator(rx, pil, c["beta"], c["hop1"], c["hop2"], c["cfg"])
+        assert all(not t.is_cuda for t in out) and out[0].dtype == torch.complex64 and out[1].dtype == torch.float64
+        mx, nmse = tol.grid_errors(out[0].numpy(), c["ref"][f"{variant}_grid"])
+        assert mx <= tol.GRID_MAX_REL and nmse <= tol.GRID_NMSE, (variant, mx, nmse)
+        tol.check_scalars(_scalars(out), c["ref"][f"{variant}_scalars"], float(c["cfg"].scs), _ta_margin(c, variant if variant == "cnn" else "tensorized"),
+                          tag=f"host/{variant}")
+        on_dev = mod.srs_channel_estimator(rx.cuda(), pil.cuda(), c["beta"], c["hop1"], c["hop2"], c["cfg"])
+        assert on_dev[0].is_cuda and all(torch.equal(a, b.cpu()) for a, b in zip(out, on_dev))
+        as_numpy = mod.srs_channel_estimator(rx.numpy(), pil.numpy(), c["beta"], c["hop1"], c["hop2"], c["cfg"])
+        assert all(torch.equal(a, b) for a, b in zip(out, as_numpy))
 
 
 @pytest.mark.parametrize("name", [n for n in NAMES])
