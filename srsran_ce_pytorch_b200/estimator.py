@@ -11,6 +11,7 @@ PyTorch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 import weakref
 from typing import Optional, Tuple
@@ -426,14 +427,24 @@ def srs_channel_estimator(received_rg, pilots, beta_dmrs, hop1, hop2, config, *,
     return grid[0], sc[0, 0], sc[0, 1], sc[0, 2], sc[0, 3], cfo
 
 
+_ACCEPT_HOST_ARRAYS = os.environ.get("SRSCE_ACCEPT_HOST_ARRAYS", "0") not in ("", "0")
+
+
+def accept_host_arrays(enable: bool = True) -> None:
+    """Opt in (or out) of host arrays in the ``compat`` drop-in modules; also set by SRSCE_ACCEPT_HOST_ARRAYS=1."""
+    global _ACCEPT_HOST_ARRAYS
+    _ACCEPT_HOST_ARRAYS = bool(enable)
+
+
 def srs_channel_estimator_any(received_rg, pilots, beta_dmrs, hop1, hop2, config, *, fill: str = "linear"):
-    """``srs_channel_estimator`` for callers that hold HOST arrays, as every caller of the reference does
-    (scripts/validation/validate_all.py:367-382, :543): CPU tensors (or numpy arrays) are copied to the current CUDA
-    device, the estimate runs there, and the six results come back as CPU tensors -- so the reference's scripts run
-    unmodified on top of ``compat/``.  CUDA tensors go straight through.  This is a transfer, not a fallback: without
-    a CUDA device it raises, there is no CPU compute path."""
+    """The entry point of the ``compat`` modules.  CUDA tensors go straight to ``srs_channel_estimator``.  HOST
+    arrays are refused by default (no CPU fallback -- raise on CPU tensors).  After ``accept_host_arrays()``
+    (or with SRSCE_ACCEPT_HOST_ARRAYS=1) CPU tensors / numpy arrays -- what every caller of the reference holds
+    (scripts/validation/validate_all.py:367-382, :543) -- are copied to the current CUDA device, estimated there, and
+    the six results come back as CPU tensors, so the reference's scripts run unmodified on top of ``compat/``.  That
+    is a transfer, not a fallback: without a CUDA device the call raises, there is no CPU compute path."""
     rx = torch.as_tensor(received_rg)
-    if rx.is_cuda:
+    if rx.is_cuda or not _ACCEPT_HOST_ARRAYS:
         return srs_channel_estimator(rx, pilots, beta_dmrs, hop1, hop2, config, fill=fill)
     if not torch.cuda.is_available():
         raise RuntimeError("srsran_ce_pytorch_b200 needs a CUDA device (sm_100a): host arrays are copied to it and back, "

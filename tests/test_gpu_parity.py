@@ -54,8 +54,9 @@ def test_rule_estimator_matches_reference(name):
 
 def test_zero_code_switch_with_host_arrays():
     """with compat/ ahead of the reference's src/ on sys.path, ``from ce_rule_tensorized import
-    ...`` serves the reference's own call shape -- HOST tensors (or numpy arrays) in, CPU tensors out, as
-    scripts/validation/validate_all.py:367-382 / :543 / :549-561 use it -- with the arithmetic on the GPU."""
+    ...`` works; after the opt-in ``accept_host_arrays()`` it serves the reference's own call shape -- HOST tensors (or
+    numpy arrays) in, CPU tensors out, as scripts/validation/validate_all.py:367-382 / :543 / :549-561 use it -- with the
+    arithmetic on the GPU.  Without the opt-in CPU tensors raise."""
     import importlib
     import sys
     compat_dir = str(ROOT / "srsran_ce_pytorch_b200" / "compat")
@@ -66,12 +67,23 @@ def test_zero_code_switch_with_host_arrays():
         sys.path.remove(compat_dir)
         for n in ("ce_rule_tensorized", "ce_rule_baseline", "ce_dl_cnn"):
             sys.modules.pop(n, None)
+    from srsran_ce_pytorch_b200 import estimator
     c = load_case(NAMES[0])
+    rx, pil = torch.as_tensor(c["rx"]).cpu(), torch.as_tensor(c["pilots"]).cpu()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):               # the default: CPU tensors are refused
+        mods[0].srs_channel_estimator(rx, pil, c["beta"], c["hop1"], c["hop2"], c["cfg"])
+    estimator.accept_host_arrays(True)
+    try:
+        _host_array_calls(mods, c, rx, pil)
+    finally:
+        estimator.accept_host_arrays(False)
+
+
+def _host_array_calls(mods, c, rx, pil):
     for mod, variant in zip(mods, ("tensorized", "baseline", "cnn")):
         if f"{variant}_grid" not in c["ref"]:
             continue
         assert {"HopConfig", "EstimatorConfig", "srs_channel_estimator"} <= set(dir(mod))
-        rx, pil = torch.as_tensor(c["rx"]).cpu(), torch.as_tensor(c["pilots"]).cpu()
         out = mod.srs_channel_estimator(rx, pil, c["beta"], c["hop1"], c["hop2"], c["cfg"])
         assert all(not t.is_cuda for t in out) and out[0].dtype == torch.complex64 and out[1].dtype == torch.float64
         mx, nmse = tol.grid_errors(out[0].numpy(), c["ref"][f"{variant}_grid"])

@@ -117,8 +117,14 @@ def test_no_cpu_fallback():
         estimator.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, synth.no_hop(), cfg)
     if not torch.cuda.is_available():
         from srsran_ce_pytorch_b200.compat import ce_rule_tensorized
-        with pytest.raises(RuntimeError, match="no CPU compute path"):      # the compat layer copies host arrays to a GPU;
-            ce_rule_tensorized.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, synth.no_hop(), cfg)   # without one it raises
+        with pytest.raises(RuntimeError, match="no CPU fallback"):          # compat modules: CPU tensors refused by default
+            ce_rule_tensorized.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, synth.no_hop(), cfg)
+        estimator.accept_host_arrays(True)                                   # opt-in: host arrays are copied to a GPU --
+        try:                                                                 # without one the call still raises
+            with pytest.raises(RuntimeError, match="no CPU compute path"):
+                ce_rule_tensorized.srs_channel_estimator(data["rx"][0], data["pilots"][0], 1.0, hop1, synth.no_hop(), cfg)
+        finally:
+            estimator.accept_host_arrays(False)
         plan = estimator.make_plan(25, 14, 1, hop1, synth.no_hop(), cfg)
         assert plan.info.has_device == 0
         import ctypes as C
