@@ -526,26 +526,25 @@ def run_config4(args):
     n_e2e = min(n_units, 2048)
     h_h = h[:n_e2e].cpu().pin_memory()
     h_out = torch.empty((n_e2e, i.n_sc, N_SYM, LAYERS), dtype=torch.complex64).pin_memory()
-    chunk, streams = 256, [torch.cuda.Stream(device=dev) for _ in range(2)]
-    d_h = [torch.empty((chunk, 1, i.n_re, LAYERS), dtype=torch.complex64, device=dev) for _ in streams]
-    d_o = [torch.empty((chunk, i.n_sc, N_SYM, LAYERS), dtype=torch.complex64, device=dev) for _ in streams]
+    from srsran_ce_pytorch_b200.hostio import FillHostPipeline
+    want64 = plan.fill(h[:64], impl="tensor").cpu()
 
-    def e2e_pass():
-        for k, b0 in enumerate(range(0, n_e2e, chunk)):
-            sidx = k % 2
-            with torch.cuda.stream(streams[sidx]):
-                d_h[sidx].copy_(h_h[b0:b0 + chunk], non_blocking=True)
-                plan.fill(d_h[sidx], impl="tensor", out=d_o[sidx])
-                h_out[b0:b0 + chunk].copy_(d_o[sidx], non_blocking=True)
-        for st in streams:
-            st.synchronize()
+    def e2e_of(pipe):
+        h_out.fill_(float("nan"))
+        pipe.run(h_h, h_out)
+        w0 = time.perf_counter()
+        for _ in range(3):
+            pipe.run(h_h, h_out)
+        dt = (time.perf_counter() - w0) / 3
+        # (the direct and the tensor implementation agree to float32 rounding, not bit for bit: compare accordingly)
+        same = bool(torch.equal(h_out[:64], want64)) if pipe.replicate == "device" else \
+            bool(torch.equal(torch.view_as_real(h_out[:64]), torch.view_as_real(plan.fill(h[:64], impl="direct").cpu())))
+        return dt, same and not bool(torch.isnan(torch.view_as_real(h_out[-1])).any()), pipe.h2d_bytes, pipe.d2h_bytes
 
-    e2e_pass()
-    w0 = time.perf_counter()
-    for _ in range(3):
-        e2e_pass()
-    e2e_s = (time.perf_counter() - w0) / 3
-    e2e_ok = bool(torch.equal(h_out[:64], plan.fill(h[:64], impl="tensor").cpu()))
+    # the tensor-core fill writes the dense grid on the device and the whole grid crosses PCIe ...
+    dense_s, dense_ok, dense_h2d, dense_d2h = e2e_of(FillHostPipeline(plan, 256, dev, n_streams=2, replicate="device", impl="tensor"))
+    # ... or (the entry point's default) the per-hop columns cross PCIe and host threads replicate them over the symbols
+    e2e_s, e2e_ok, e2e_h2d, e2e_d2h = e2e_of(FillHostPipeline(plan, 256, dev, n_streams=3, replicate="host"))
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -579,8 +578,12 @@ def run_config4(args):
                         "what": "same operator with float32 FMAs in the fused kernel's writer warps (srsce_fill direct)"},
         "full_ce_dl_cnn_estimator": {"value": LAYERS * rx.shape[0] / (ms_e * 1e-3), "unit": UNIT, "kernel_ms": ms_e, "units": rx.shape[0],
                                      "roofline_frac": algorithmic_bytes_per_unit() * rx.shape[0] / (ms_e * 1e-3) / 1e9 / peak},
-        "e2e": {"value": LAYERS * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": n_e2e * i.n_re * LAYERS * 8,
-                "d2h_bytes_per_step": n_e2e * i.n_sc * N_SYM * LAYERS * 8, "units_per_step": n_e2e, "matches_device_path": e2e_ok},
+        "e2e": {"value": LAYERS * n_e2e / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                "units_per_step": n_e2e, "replication": "host (srsce_fill_compact + srsce_replicate_host)",
+                "grid_bit_identical_to_device_path": e2e_ok,
+                "dense_copy": {"value": LAYERS * n_e2e / dense_s, "unit": UNIT, "h2d_bytes_per_step": dense_h2d,
+                               "d2h_bytes_per_step": dense_d2h, "grid_bit_identical_to_device_path": dense_ok,
+                               "note": "fill_tc_kernel writes the dense grid on the device and the whole grid crosses PCIe"}},
         "gpu_launches": launches_timed, "clocks": sampler.summary(wall0, wall1),
     }
     if cpu is not None:

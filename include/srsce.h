@@ -184,6 +184,12 @@ int srsce_estimate_indexed(const srsce_plan* plan, const void* rx_grids, const i
 enum { SRSCE_FILL_IMPL_DIRECT = 0, SRSCE_FILL_IMPL_TENSOR = 1 };
 int srsce_fill(const srsce_plan* plan, const void* h_pilots, void* ch_est, int64_t n_units, int32_t impl, void* stream);
 
+/* srsce_fill (direct implementation) with the output left as per-hop columns, like srsce_estimate_compact:
+ *   ch_sc  complex64 [n_units][n_hops][n_sc][n_layers]: the interpolated band of each hop (0 outside it); the replication
+ *          over the allocated symbols (:346-347) is left to the consumer -- srsce_replicate_host(..., SRSCE_REPLICATE_FILL)
+ *          for a caller that wants the dense grid in host memory.  Not part of the reference contract. */
+int srsce_fill_compact(const srsce_plan* plan, const void* h_pilots, void* ch_sc, int64_t n_units, void* stream);
+
 /* EXTENSION (no counterpart in the reference, which takes the pilots as an input tensor,
  * ce_rule_tensorized.py:746-747 -- parity unpinned): low-PAPR pilot sequences of TS 38.211 5.2.2 generated on the device
  * in the estimator's pilot layout.
@@ -203,10 +209,14 @@ int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, i
  *   ch_est     HOST complex64 [n_units][n_sc][n_sym][n_layers], fully overwritten -- bit-identical to what
  *              srsce_estimate writes on the device for the same inputs
  *   n_threads  host threads to use (<= 0: all the cores); a small persistent pool inside the library
+ *   flags      0, or SRSCE_REPLICATE_FILL: the columns come from srsce_fill_compact (the fill never rotates)
  * It performs NO arithmetic, only the copy: a plan whose grid carries the per-symbol CFO rotation (:922-929; cfo_defined
- * and cfo_compensate) fails with SRSCE_ERR_UNSUPPORTED -- such plans take srsce_estimate and a dense device->host copy.
+ * and cfo_compensate) fails with SRSCE_ERR_UNSUPPORTED unless SRSCE_REPLICATE_FILL is set -- such plans take
+ * srsce_estimate and a dense device->host copy.
  * Needs no CUDA device; blocking; may be called from several threads (calls are serialised on the pool). */
-int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads);
+enum { SRSCE_REPLICATE_FILL = 1 };
+int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads,
+                         int32_t flags);
 
 /* Number of kernel launches the last srsce_estimate on this thread issued (bench bookkeeping). */
 int srsce_last_launch_count(void);

@@ -18,6 +18,7 @@ ABI_VERSION = 3
 SMOOTH = {"none": 0, "mean": 1, "filter": 2}
 FILL_LINEAR, FILL_CNN = 0, 1
 FILL_IMPL = {"direct": 0, "tensor": 1}
+REPLICATE_FILL = 1
 
 ERR_INVALID, ERR_ASSERT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA = -1, -2, -3, -4, -5
 
@@ -76,7 +77,9 @@ def _load() -> C.CDLL:
     lib.srsce_fill.restype = C.c_int
     lib.srsce_gen_pilots.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.srsce_gen_pilots.restype = C.c_int
-    lib.srsce_replicate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+    lib.srsce_fill_compact.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.srsce_fill_compact.restype = C.c_int
+    lib.srsce_replicate_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]
     lib.srsce_replicate_host.restype = C.c_int
     lib.srsce_last_launch_count.restype = C.c_int
     if lib.srsce_abi_version() != ABI_VERSION:
@@ -87,7 +90,7 @@ def _load() -> C.CDLL:
 lib = _load()
 
 EXPORTS = ("srsce_abi_version", "srsce_last_error", "srsce_plan_create", "srsce_plan_destroy", "srsce_plan_query",
-           "srsce_plan_tables", "srsce_plan_fill_tensor_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed", "srsce_fill", "srsce_gen_pilots", "srsce_replicate_host",
+           "srsce_plan_tables", "srsce_plan_fill_tensor_tables", "srsce_estimate", "srsce_estimate_compact", "srsce_estimate_indexed", "srsce_fill", "srsce_fill_compact", "srsce_gen_pilots", "srsce_replicate_host",
            "srsce_last_launch_count")
 
 

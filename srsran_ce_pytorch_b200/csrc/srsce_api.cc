@@ -217,7 +217,24 @@ int srsce_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, i
   return rc == SRSCE_OK ? rc : fail(rc, err);
 }
 
-int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads) {
+int srsce_fill_compact(const srsce_plan* plan, const void* h_pilots, void* ch_sc, int64_t n_units, void* stream) {
+  g_launches = 0;
+  if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
+  if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
+  if (n_units > 0 && (!h_pilots || !ch_sc)) return fail(SRSCE_ERR_INVALID, "null buffer");
+  if ((reinterpret_cast<uintptr_t>(ch_sc) & 7u) || (reinterpret_cast<uintptr_t>(h_pilots) & 7u))
+    return fail(SRSCE_ERR_INVALID, "buffers must be 8-byte aligned");
+  try {
+    std::string err;
+    const int rc = srsce::launch_fill_direct(plan->impl, h_pilots, nullptr, n_units, stream, &g_launches, err, ch_sc);
+    return rc == SRSCE_OK ? rc : fail(rc, err);
+  } catch (const std::exception& e) {
+    return fail(SRSCE_ERR_INVALID, e.what());
+  }
+}
+
+int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est, int64_t n_units, int32_t n_threads,
+                         int32_t flags) {
   if (!plan) return fail(SRSCE_ERR_INVALID, "null argument");
   if (n_units < 0) return fail(SRSCE_ERR_INVALID, "negative unit count");
   if (n_units > 0 && (!ch_sc || !ch_est)) return fail(SRSCE_ERR_INVALID, "null buffer");
@@ -225,7 +242,7 @@ int srsce_replicate_host(const srsce_plan* plan, const void* ch_sc, void* ch_est
     return fail(SRSCE_ERR_INVALID, "buffers must be 8-byte aligned");
   try {
     std::string err;
-    const int rc = srsce::replicate_host(plan->impl, ch_sc, ch_est, n_units, n_threads, err);
+    const int rc = srsce::replicate_host(plan->impl, ch_sc, ch_est, n_units, n_threads, flags, err);
     return rc == SRSCE_OK ? rc : fail(rc, err);
   } catch (const std::exception& e) {
     return fail(SRSCE_ERR_INVALID, e.what());

@@ -180,9 +180,10 @@ void replicate_rows(const Replicate& j, int64_t row0, int64_t row1) {
 
 }  // namespace
 
-int replicate_host(const Plan& plan, const void* ch_sc, void* ch_est, int64_t n_units, int n_threads, std::string& err) {
+int replicate_host(const Plan& plan, const void* ch_sc, void* ch_est, int64_t n_units, int n_threads, int flags,
+                   std::string& err) {
   const PlanDev& v = plan.dev;
-  if (v.cfo_compensate && v.cfo_defined) {
+  if (v.cfo_compensate && v.cfo_defined && !(flags & SRSCE_REPLICATE_FILL)) {
     err = "this plan's grid carries the per-symbol CFO rotation: the host side only replicates, use srsce_estimate";
     return SRSCE_ERR_UNSUPPORTED;
   }

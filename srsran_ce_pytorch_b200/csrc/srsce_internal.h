@@ -172,11 +172,12 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
                     void* rot_compact = nullptr, const int64_t* rx_index = nullptr);
 int max_dynamic_smem();
 int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
-                       std::string& err);
+                       std::string& err, void* out_compact = nullptr);
 
 // srsce_seq.cu
 // srsce_hostio.cc: replication of the compact per-hop columns over the allocated symbols, in host memory, on host threads
-int replicate_host(const Plan& plan, const void* ch_sc, void* ch_est, int64_t n_units, int n_threads, std::string& err);
+int replicate_host(const Plan& plan, const void* ch_sc, void* ch_est, int64_t n_units, int n_threads, int flags,
+                   std::string& err);
 int launch_gen_pilots(void* pilots, int64_t n_ue, int32_t m_zc, int32_t n_dmrs, int32_t n_layers, const int32_t* u_of,
                       const int32_t* v_of, void* stream, std::string& err);
 int largest_prime_below(int m);

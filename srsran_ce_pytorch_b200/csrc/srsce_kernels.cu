@@ -1403,7 +1403,7 @@ int launch_estimate(const Plan& p, const void* rx, const int64_t strides[3], con
 
 // srsce_fill, direct implementation: the fused kernel's writer warps fed with given smoothed pilots (no phase A).
 int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n_units, void* stream, int* launches,
-                       std::string& err) {
+                       std::string& err, void* out_compact) {
   *launches = 0;
   if (p.device < 0) { err = "plan has no CUDA device (created without a GPU); there is no CPU compute path"; return SRSCE_ERR_NO_DEVICE; }
   int dev = -1;
@@ -1418,8 +1418,8 @@ int launch_fill_direct(const Plan& p, const void* h_pilots, void* out, int64_t n
   float2* h_scratch = nullptr;
   if (int rc = alloc_h_scratch(v, grid, stream, &h_scratch, err)) return rc;
   fn<<<grid, cta_threads(v.est_threads, v.n_hops == 2), v.smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-      v, nullptr, 0, 0, 0, nullptr, 1, 1.0, static_cast<float2*>(out), nullptr, (long long)n_units, 0, nullptr, nullptr,
-      nullptr, static_cast<const float2*>(h_pilots), h_scratch);
+      v, nullptr, 0, 0, 0, nullptr, 1, 1.0, static_cast<float2*>(out), nullptr, (long long)n_units, 0,
+      static_cast<float2*>(out_compact), nullptr, nullptr, static_cast<const float2*>(h_pilots), h_scratch);
   cudaError_t e = cudaGetLastError();
   if (h_scratch) cudaFreeAsync(h_scratch, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { err = cuda_msg("fill launch", e); return SRSCE_ERR_CUDA; }

@@ -201,11 +201,7 @@ class Plan:
                                                       scalars.data_ptr(), n_units, C.c_void_p(stream)))
         return ch, rot, scalars
 
-    def fill(self, h_pilots: torch.Tensor, impl: str = "direct", out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """The fill operator alone (``srsce_fill``): h_pilots [B, n_hops, n_re, L] complex64 (the smoothed pilot
-        estimates of each hop) -> dense [B, n_sc, n_sym, L] grid, zero outside the band / allocated symbols.
-        ``impl`` = "direct" (float32 FMAs in the fused kernel's writer warps) or "tensor" (tcgen05 banded GEMM;
-        raises NotImplementedError when ``info.fill_tensor`` is 0)."""
+    def _check_fill_input(self, h_pilots: torch.Tensor) -> Tuple[int, int, torch.Tensor]:
         i = self.info
         n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
         if not h_pilots.is_cuda:
@@ -214,10 +210,17 @@ class Plan:
             raise TypeError("h_pilots must be complex64")
         if h_pilots.dim() != 4 or tuple(h_pilots.shape[1:]) != (n_hops, i.n_re, i.n_layers):
             raise IndexError(f"h_pilots shape {tuple(h_pilots.shape)} != [B, {n_hops}, {i.n_re}, {i.n_layers}]")
+        return int(h_pilots.shape[0]), n_hops, self._materialize(h_pilots).contiguous()
+
+    def fill(self, h_pilots: torch.Tensor, impl: str = "direct", out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The fill operator alone (``srsce_fill``): h_pilots [B, n_hops, n_re, L] complex64 (the smoothed pilot
+        estimates of each hop) -> dense [B, n_sc, n_sym, L] grid, zero outside the band / allocated symbols.
+        ``impl`` = "direct" (float32 FMAs in the fused kernel's writer warps) or "tensor" (tcgen05 banded GEMM;
+        raises NotImplementedError when ``info.fill_tensor`` is 0)."""
+        i = self.info
         if impl not in _lib.FILL_IMPL:
             raise ValueError(f"unknown fill implementation {impl!r}")
-        h_pilots = self._materialize(h_pilots).contiguous()
-        n_units = int(h_pilots.shape[0])
+        n_units, _, h_pilots = self._check_fill_input(h_pilots)
         if out is None:
             out = torch.empty((n_units, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64, device=h_pilots.device)
         elif tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers) or not out.is_contiguous() \
@@ -229,10 +232,23 @@ class Plan:
                                           C.c_void_p(stream)))
         return out
 
-    def replicate_host(self, ch: torch.Tensor, out: torch.Tensor, n_threads: int = 0) -> torch.Tensor:
+    def fill_compact(self, h_pilots: torch.Tensor) -> torch.Tensor:
+        """``srsce_fill_compact``: the fill with the output left as per-hop columns [B, n_hops, n_sc, L] (the band of
+        each hop interpolated, zero outside it); ``expand_compact(ch, ones)`` or ``replicate_host(ch, out,
+        from_fill=True)`` rebuild the dense grid of ``fill``."""
+        i = self.info
+        n_units, n_hops, h_pilots = self._check_fill_input(h_pilots)
+        ch = torch.empty((n_units, n_hops, i.n_sc, i.n_layers), dtype=torch.complex64, device=h_pilots.device)
+        with torch.cuda.device(h_pilots.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.raise_for(lib.srsce_fill_compact(self._h, h_pilots.data_ptr(), ch.data_ptr(), n_units, C.c_void_p(stream)))
+        return ch
+
+    def replicate_host(self, ch: torch.Tensor, out: torch.Tensor, n_threads: int = 0, from_fill: bool = False) -> torch.Tensor:
         """``srsce_replicate_host``: HOST tensors ch [B, n_hops, n_sc, L] (``estimate_compact``'s first output, copied
         to the host) -> the dense [B, n_sc, n_sym, L] grid in ``out`` (host), written by the library's host threads.
-        A copy, no arithmetic: plans with a final CFO rotation raise NotImplementedError (use ``estimate``)."""
+        A copy, no arithmetic: plans with a final CFO rotation raise NotImplementedError (use ``estimate``) unless the
+        columns come from ``fill_compact`` (``from_fill=True``: the fill never rotates)."""
         i = self.info
         n_hops = 2 if self.desc.hop[1].dmrs_symbol_mask else 1
         for t in (ch, out):
@@ -243,7 +259,8 @@ class Plan:
             raise IndexError(f"ch shape {tuple(ch.shape)} != [B, {n_hops}, {i.n_sc}, {i.n_layers}]")
         if tuple(out.shape) != (n_units, i.n_sc, i.n_sym, i.n_layers):
             raise IndexError(f"out shape {tuple(out.shape)} != [{n_units}, {i.n_sc}, {i.n_sym}, {i.n_layers}]")
-        _lib.raise_for(lib.srsce_replicate_host(self._h, ch.data_ptr(), out.data_ptr(), n_units, int(n_threads)))
+        _lib.raise_for(lib.srsce_replicate_host(self._h, ch.data_ptr(), out.data_ptr(), n_units, int(n_threads),
+                                                _lib.REPLICATE_FILL if from_fill else 0))
         return out
 
     @property

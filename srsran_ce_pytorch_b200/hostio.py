@@ -132,3 +132,70 @@ def srs_channel_estimator_host(plan: Plan, rx, pilots, beta_dmrs: float, pilot_s
     out = torch.empty((n, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64).pin_memory()
     sc = torch.empty((n, 6), dtype=torch.float64).pin_memory()
     return pipe.run(rx, pilots, float(beta_dmrs), out, sc)
+
+
+class FillHostPipeline:
+    """The fill seam for a caller that holds host arrays: smoothed pilots [B, n_hops, n_re, L] in host memory in, dense
+    grids [B, n_sc, n_sym, L] in host memory out (``srsce_fill`` semantics).  ``replicate="host"`` (default): the
+    per-hop columns of ``srsce_fill_compact`` cross PCIe and ``srsce_replicate_host`` rebuilds the grid (the fill has no
+    CFO rotation, so this is always a pure copy); ``"device"``: ``srsce_fill`` writes the dense grid on the device
+    (``impl`` direct or tensor) and the whole grid crosses the link."""
+
+    def __init__(self, plan: Plan, chunk_units: int = 256, device: Optional[torch.device] = None, n_streams: int = 3,
+                 replicate: str = "host", impl: str = "direct", host_threads: int = 0):
+        if replicate not in ("device", "host"):
+            raise ValueError(f"unknown replicate mode {replicate!r}")
+        i = plan.info
+        n_hops = 2 if plan.desc.hop[1].dmrs_symbol_mask else 1
+        self.plan, self.chunk, self.replicate, self.impl, self.host_threads = plan, int(chunk_units), replicate, impl, int(host_threads)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        c64, dev = torch.complex64, self.device
+        self.d_h = [torch.empty((self.chunk, n_hops, i.n_re, i.n_layers), dtype=c64, device=dev) for _ in self.streams]
+        if replicate == "host":
+            self.h_ch = [torch.empty((self.chunk, n_hops, i.n_sc, i.n_layers), dtype=c64).pin_memory() for _ in self.streams]
+            self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="srsce-replicate")
+        else:
+            self.d_out = [torch.empty((self.chunk, i.n_sc, i.n_sym, i.n_layers), dtype=c64, device=dev) for _ in self.streams]
+        self.h2d_bytes = self.d2h_bytes = self.launches = 0
+
+    def run(self, h_pilots: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        if h_pilots.is_cuda or out.is_cuda:
+            raise ValueError("FillHostPipeline takes host tensors; call Plan.fill for device tensors")
+        n = int(h_pilots.shape[0])
+        self.h2d_bytes = self.d2h_bytes = self.launches = 0
+        pending = [None] * len(self.streams)
+        for k, b0 in enumerate(range(0, n, self.chunk)):
+            b1 = min(n, b0 + self.chunk)
+            m = b1 - b0
+            s = k % len(self.streams)
+            if pending[s] is not None:
+                pending[s].result()
+                pending[s] = None
+            with torch.cuda.stream(self.streams[s]):
+                d_h = self.d_h[s][:m]
+                d_h.copy_(h_pilots[b0:b1], non_blocking=True)
+                if self.replicate == "host":
+                    ch = self.plan.fill_compact(d_h)
+                    self.h_ch[s][:m].copy_(ch, non_blocking=True)
+                    ch.record_stream(self.streams[s])
+                    landed = torch.cuda.Event()
+                    landed.record(self.streams[s])
+                    pending[s] = self._worker.submit(self._replicate, landed, self.h_ch[s][:m], out[b0:b1])
+                    self.d2h_bytes += ch.numel() * 8
+                else:
+                    self.plan.fill(d_h, impl=self.impl, out=self.d_out[s][:m])
+                    out[b0:b1].copy_(self.d_out[s][:m], non_blocking=True)
+                    self.d2h_bytes += m * self.d_out[s][0].numel() * 8
+            self.h2d_bytes += d_h.numel() * 8
+            self.launches += 1
+        for f in pending:
+            if f is not None:
+                f.result()
+        for st in self.streams:
+            st.synchronize()
+        return out
+
+    def _replicate(self, landed: torch.cuda.Event, ch_host: torch.Tensor, out: torch.Tensor) -> None:
+        landed.synchronize()
+        self.plan.replicate_host(ch_host, out, self.host_threads, from_fill=True)

@@ -186,3 +186,37 @@ def test_fill_random_masks_match_oracle(k):
             if B > 2:                                         # batch independence: the last unit equals a batch of its own
                 solo = plan.fill(h[-1:].cuda(), impl=impl)
                 assert torch.equal(solo[0], out[-1]), (FUZZ[k], fill, impl)
+
+
+@pytest.mark.parametrize("case", [FILL_CASES[0], FILL_CASES[1], FILL_CASES[4], FILL_CASES[9]], ids=["f0", "f1", "f4", "f9"])
+@pytest.mark.parametrize("fill", ["linear", "cnn"])
+def test_fill_compact_and_host_pipeline(case, fill):
+    """srsce_fill_compact leaves the fill as per-hop columns; replicated over the allocated symbols (on the device by
+    ``expand_compact``, on the host by ``srsce_replicate_host``) they are bit-identical to srsce_fill's dense grid.
+    FillHostPipeline (host arrays in / out) returns the same grid in both replication modes, including a partial
+    last chunk, and for a plan whose estimator output would carry a CFO rotation (the fill never rotates)."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    from srsran_ce_pytorch_b200.hostio import FillHostPipeline
+    grid, start, n, pat, L, s0, na, units = case
+    hop1 = synth.make_hop(grid, start, n, [s0 + 1, s0 + 3] if na >= 4 else [s0], pat, (L + 1) // 2, start_symbol=s0, n_alloc=na)
+    cfg = synth.make_config(30e3, "filter", True)
+    plan = estimator.make_plan(grid, 14, L, hop1, synth.no_hop(), cfg, fill)
+    i = plan.info
+    g = torch.Generator(device="cuda").manual_seed(3)
+    h = torch.view_as_complex(torch.randn((units, 1, i.n_re, L, 2), device="cuda", generator=g))
+    dense = plan.fill(h, impl="direct")
+    ch = plan.fill_compact(h)
+    assert ch.shape == (units, 1, i.n_sc, L)
+    ones = torch.ones((units, 14), dtype=torch.complex64, device="cuda")
+    assert torch.equal(torch.view_as_real(plan.expand_compact(ch, ones)), torch.view_as_real(dense))
+    h_host = h.cpu().pin_memory()
+    out = torch.full(dense.shape, float("nan"), dtype=torch.complex64).pin_memory()
+    for mode in ("host", "device"):
+        pipe = FillHostPipeline(plan, 16, n_streams=2, replicate=mode)
+        out.fill_(float("nan"))
+        pipe.run(h_host, out)
+        assert torch.equal(torch.view_as_real(out), torch.view_as_real(dense.cpu())), mode
+        assert pipe.launches == (units + 15) // 16
+    if plan.has_final_rotation:
+        with pytest.raises(NotImplementedError):
+            plan.replicate_host(ch.cpu(), out)                    # estimator columns of this plan would need the rotation

@@ -82,6 +82,9 @@ def test_replicate_host_refuses_plans_with_a_final_rotation_and_bad_buffers():
     out = torch.zeros((1, i.n_sc, 14, 2), dtype=torch.complex64)
     with pytest.raises(NotImplementedError):
         plan.replicate_host(ch, out)
+    ch = _columns(plan, 1, seed=2)                                         # columns of srsce_fill_compact: never rotated
+    plan.replicate_host(ch, out, from_fill=True)
+    assert torch.equal(torch.view_as_real(out), torch.view_as_real(plan.expand_compact(ch, torch.ones((1, 14), dtype=torch.complex64))))
     plan2 = _plan(CASES[1])
     i2 = plan2.info
     with pytest.raises(IndexError):
