@@ -128,7 +128,7 @@ def srs_channel_estimator_host(plan: Plan, rx, pilots, beta_dmrs: float, pilot_s
     """Convenience wrapper: allocate pinned outputs and run one pipelined pass."""
     i = plan.info
     n = int(rx.shape[0])
-    pipe = pipeline or HostPipeline(plan, min(chunk_units, max(pilot_share, n)), pilot_share, replicate="auto")
+    pipe = pipeline or HostPipeline(plan, min(chunk_units, max(pilot_share, n)), pilot_share, n_streams=3, replicate="auto")
     out = torch.empty((n, i.n_sc, i.n_sym, i.n_layers), dtype=torch.complex64).pin_memory()
     sc = torch.empty((n, 6), dtype=torch.float64).pin_memory()
     return pipe.run(rx, pilots, float(beta_dmrs), out, sc)
