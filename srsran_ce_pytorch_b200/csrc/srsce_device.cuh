@@ -58,6 +58,23 @@ __device__ __forceinline__ void stream_full_tile_odd(const float2* __restrict__ 
                                                      float2 rot1) {
   constexpr int kCols = 14 * LL / 2, kRowsPerPass = 32 / kCols, kPasses = kTileRows / kRowsPerPass;
   static_assert(kTileRows % kRowsPerPass == 0, "tile rows must split evenly over the warp passes");
+  if (LL == 1) {
+    // one layer: both elements of a slot are the SAME row value on two symbols -- one 8-byte shared load per store,
+    // all loads of the tile issued ahead of the stores (see kStreamBatch above)
+    float2 v[kPasses];
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) v[p] = (on0 || on1) ? src0[p * kRowsPerPass] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kPasses; ++p) {
+      float2 a = on0 ? v[p] : make_float2(0.f, 0.f), b = on1 ? v[p] : make_float2(0.f, 0.f);
+      if (ROT) {
+        a = cmul(a, rot0);
+        b = cmul(b, rot1);
+      }
+      __stcs(dst + p * (kRowsPerPass * kCols), make_float4(a.x, a.y, b.x, b.y));
+    }
+    return;
+  }
 #pragma unroll
   for (int p = 0; p < kPasses; ++p) {
     float2 a = on0 ? src0[p * (kRowsPerPass * LL)] : make_float2(0.f, 0.f);
