@@ -291,6 +291,7 @@ class _Acc:
     ta: float = 0.0
     cfo: Optional[float] = None
     ta_margin: list = field(default_factory=list)   # diagnostic: top-2 relative gap per hop
+    cfo_kappa: float = 1.0                          # diagnostic: worst summation condition number of a CFO correlation
 
 
 def symbol_start_times(cp_ms: np.ndarray, scs: float) -> np.ndarray:
@@ -334,6 +335,14 @@ def _hop(rx: np.ndarray, pilots: np.ndarray, beta: float, hop: HopSpec, cfg: Est
                          .astype(f64).sum())
         if n_layers % 2:
             tot += float(f32(np.angle(inner[-1])))
+        # diagnostic only (tests/tolerances.py): sum |terms| / |sum terms| of each correlation whose angle is taken --
+        # a layer with no signal leaves a float32 sum of noise products that nearly cancels, and its angle is then
+        # determined by rounding (the reference takes the angle all the same)
+        terms = (np.conj(x[:, 0, :]) * x[:, 1, :]).astype(np.complex128)
+        groups = [terms[:, k:k + 2].sum(axis=1) for k in range(0, n_even, 2)] + ([terms[:, -1]] if n_layers % 2 else [])
+        for t in groups:
+            tot_abs = abs(t.sum())
+            acc.cfo_kappa = max(acc.cfo_kappa, float(np.abs(t).sum() / tot_abs) if tot_abs > 0 else float("inf"))
         n_samp = float(sym_idx[1] - sym_idx[0]) + float(cpd[sym_idx[0] + 1: sym_idx[1] + 1].sum())
         cfo_hop = tot / (2.0 * math.pi * n_samp) / float(n_cdm)
         if cfg.cfo_compensate:
@@ -438,4 +447,5 @@ def estimate(received_rg, pilots, beta_dmrs, hop1, hop2, config, fill: str = "te
         grid = grid * rot[None, :, None]
     if diagnostics is not None:
         diagnostics["ta_margin"] = acc.ta_margin
+        diagnostics["cfo_kappa"] = acc.cfo_kappa
     return grid, noise, rsrp, epre, ta, (None if acc.cfo is None else acc.cfo * cfg.scs)

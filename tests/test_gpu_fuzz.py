@@ -71,6 +71,8 @@ def test_random_geometry_matches_oracle(k):
             if not np.isfinite(want[1]):
                 continue                                   # a single pilot in total: the reference divides by zero
             mx, nmse = tol.grid_errors(out[b], want[0])
-            assert mx <= tol.GRID_MAX_REL and nmse <= tol.grid_nmse_gate((c["s1"], c["s2"]), c["cfo"], c["sm"], c["n_prb"] * c["cols"][0].count("1")), (c, fill, b, mx, nmse)
+            gate = tol.grid_nmse_gate((c["s1"], c["s2"]), c["cfo"], c["sm"], c["n_prb"] * c["cols"][0].count("1"),
+                                      cfo_kappa=diag.get("cfo_kappa"), n_cdm=n_cdm)
+            assert mx <= tol.GRID_MAX_REL and nmse <= gate, (c, fill, b, mx, nmse, gate, diag.get("cfo_kappa"))
             got = [sc[b, 0], sc[b, 1], sc[b, 2], sc[b, 3], sc[b, 4] if sc[b, 5] else None]
             tol.check_scalars(got, want[1:], 30e3, diag["ta_margin"], tag=f"fuzz{k}/{fill}/{b}")

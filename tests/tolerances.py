@@ -15,7 +15,10 @@ CFO_REL, CFO_ABS_OF_SCS = 1e-4, 1e-7
 TA_TIE_MARGIN = 1e-5     # TA must match exactly unless the two largest profile bins are this close
 
 
-def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_pilots=None):
+EPS32 = 2.0 ** -24
+
+
+def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_pilots=None, cfo_kappa=None, n_cdm=1):
     """NMSE gate for one geometry.  With CFO compensation the reference extrapolates the phase measured between the
     first two pilot symbols of a hop (float32 correlation sum, float32 angle) over the whole slot: an angle error d
     becomes a rotation error d * (t - t0) / (t1 - t0), up to 13 / (t1 - t0) symbols of lever.  Different float32
@@ -44,6 +47,17 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_
             if syms is not None and len(syms) >= 2:
                 lever = 13.0 / float(syms[1] - syms[0])
                 gate = max(gate, GRID_NMSE * lever * lever / 4.0)
+                if cfo_kappa is not None and cfo_kappa > 1.0:
+                    # the CFO is the mean over the CDM groups of the angles of float32 correlation sums.  A sum with
+                    # condition number kappa = sum|terms| / |sum terms| (the oracle reports the worst one,
+                    # diagnostics["cfo_kappa"]) is known to ~eps32 * kappa; a layer without signal gives kappa of several
+                    # hundred, its angle is rounding noise, and every implementation (numpy, torch, the kernel) lands
+                    # elsewhere: campaign seed 4101 case 293 -- kappa 318, kernel / oracle / float32 reference -5.9e-7 /
+                    # +4.1e-7 / -2e-8 relative from the float64 reference's CFO; kernel vs the float32 REFERENCE NMSE
+                    # 3.7e-13, kernel vs oracle 1.25e-12.  Angle uncertainty taken as eps32 * kappa / 4, spread over the
+                    # slot by the lever, mean square over the symbols (1 / 3).
+                    d = 0.25 * EPS32 * min(cfo_kappa, 1e6) * lever / float(max(1, n_cdm))
+                    gate = max(gate, d * d / 3.0)
     return gate
 
 
