@@ -327,7 +327,9 @@ def _hop(rx: np.ndarray, pilots: np.ndarray, beta: float, hop: HopSpec, cfg: Est
     cfo_hop = None
     if n_dmrs >= 2:
         cpd = cfg.cp_ms.astype(f64) * (cfg.scs / 1000.0)
-        inner = (np.conj(x[:, 0, :]) * x[:, 1, :]).sum(axis=0, dtype=c64)
+        prod = np.conj(x[:, 0, :]) * x[:, 1, :]
+        # (per layer over a contiguous vector, i.e. pairwise like torch's sum -- see the mean smoothing below)
+        inner = np.array([np.ascontiguousarray(prod[:, l]).sum(dtype=c64) for l in range(n_layers)], dtype=c64)
         n_even = (n_layers // 2) * 2
         tot = 0.0
         if n_even:
@@ -364,7 +366,11 @@ def _hop(rx: np.ndarray, pilots: np.ndarray, beta: float, hop: HopSpec, cfg: Est
 
     # --- smoothing (:633-668)
     if cfg.smoothing == "mean":
-        h = np.ones_like(h) * (h.sum(axis=0, dtype=c64) / c64(h.shape[0]))[None, :]
+        # (per layer over a contiguous vector: numpy then sums pairwise, like torch's cascade sum -- a reduction along
+        #  axis 0 of the [N, L] array would accumulate row by row, and over >= 1 000 cancelling pilots that sequential
+        #  float32 sum is 30x further from the float64 result than the reference's own float32 mean)
+        mean = np.array([np.ascontiguousarray(h[:, l]).sum(dtype=c64) for l in range(h.shape[1])], dtype=c64) / c64(h.shape[0])
+        h = np.ones_like(h) * mean[None, :]
     elif cfg.smoothing == "filter":
         taps = rc_taps(12 // per_prb, min(3, n_prb_mask))
         nv = n_virtual(taps.size, n_prb_mask, per_prb)

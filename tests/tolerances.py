@@ -31,11 +31,12 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_
         # the whole band collapses to the float32 mean of N pilots whose phases rotate across the band: the mean can
         # be ~10x smaller than its terms, and numpy's pairwise sum vs the kernel's per-thread partial sums then differ
         # by ~1e-6 of it (1 of 1200 random geometries: constant error 9e-8 on a layer of mean magnitude 0.05).
-        # This gate holds for the campaign's sizes (<= 106 PRB).  It is a conditioning rule, not a constant: on the
-        # synthetic 100-sample delay spread the mean of >= 3 276 pilots (dense mask at 273 / 341 PRB) cancels to ~1 % of
-        # its terms and kernel vs oracle reach NMSE 8e-11 / 4e-10 on every layout (tools/mean_probe.py) -- the kernel
-        # sums float32 partials of 8 terms and then float64, numpy sums pairwise in float32, torch in its own order.
-        # Tests of mean smoothing at those sizes use a nearly flat channel (max_delay = 1).
+        # The summation ORDER matters as much as the precision here: over >= 1 000 pilots of the synthetic 100-sample
+        # delay spread the mean cancels to ~1 % of its terms; the reference's float32 mean (torch's cascade sum) stays
+        # within 3e-12 NMSE of its own float64 result, a row-by-row float32 accumulation is 30x further off.  The oracle
+        # therefore sums each layer pairwise (oracle/ce_oracle.py), the kernel sums float32 partials of 8 terms and then
+        # float64; kernel vs oracle at 106 / 273 / 341 PRB with the dense mask: NMSE <= 6e-13 / 4e-12 / 6e-12
+        # (tools/mean_probe.py), inside this gate.
         gate = 10.0 * GRID_NMSE
     if smoothing == "filter" and n_pilots is not None and n_pilots <= 12:
         # every output sits next to the virtual pilots, which extrapolate float32 `angle` values (CUDA atan2f: <= 2 ulp,

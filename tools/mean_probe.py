@@ -1,5 +1,5 @@
-"""Mean smoothing at large pilot counts: kernel vs oracle NMSE on the synthetic 100-sample delay spread (float32 cancellation
-of the band mean; see tests/tolerances.py).  Prints the worst NMSE over 24 units per geometry."""
+"""Mean smoothing at large pilot counts: kernel vs oracle NMSE on the synthetic 100-sample delay spread (the band mean
+cancels to ~1 % of its terms, so float32 summation order shows; see tests/tolerances.py).  Worst NMSE over 24 units per geometry."""
 import sys; from pathlib import Path; sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 from oracle import ce_oracle
