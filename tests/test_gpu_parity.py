@@ -466,6 +466,47 @@ def test_host_pipeline_with_host_side_replication(two_hops):
     assert HostPipeline(planr, 8, 4, replicate="auto").replicate == "device"
 
 
+@pytest.mark.parametrize("global_h", [False, True], ids=["smem-h", "global-h"])
+def test_one_plan_shared_by_threads_and_streams(global_h):
+    """include/srsce.h: a plan is immutable and may be shared by threads and streams.  Four threads, each on its own
+    stream, run the same plan on different inputs at the same time (for the layout-F plan every launch takes its own
+    stream-ordered scratch); every result equals the one computed alone."""
+    import threading
+    from srsran_ce_pytorch_b200 import estimator, synth
+    if global_h:
+        hop1 = synth.make_hop(273, 0, 273, [3], "dense", 2, start_symbol=0, n_alloc=7)
+        hop2 = synth.make_hop(273, 0, 273, [10], "dense", 2, start_symbol=7, n_alloc=7)
+        n = 160
+    else:
+        hop1, hop2, n = synth.make_hop(273, 0, 273, [13], "comb4", 2), synth.no_hop(), 320
+    cfg = synth.make_config(30e3, "filter", True)
+    plan = estimator.make_plan(273, 14, 4, hop1, hop2, cfg)
+    assert bool(plan.info.h_in_global) == global_h
+    inputs = [synth.make_units(hop1, hop2, cfg, 4, n, pilot_share=4, seed=20 + k, device="cuda") for k in range(4)]
+    alone = [plan.estimate(d["rx"], d["pilots"], 1.0, 4) for d in inputs]
+    torch.cuda.synchronize()
+    results, errors = [None] * 4, []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(3):
+                    results[k] = plan.estimate(inputs[k]["rx"], inputs[k]["pilots"], 1.0, 4)
+            st.synchronize()
+        except Exception as e:          # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k in range(4):
+        assert torch.equal(results[k][0], alone[k][0]) and torch.equal(results[k][1], alone[k][1]), k
+
+
 @pytest.mark.parametrize("syms", [(13,), (3, 10)], ids=["single-cta", "cta-pair"])
 def test_unit_counts_around_the_resident_cta_count(syms):
     """Launches of 1 ... 2 x SMs + 1 units: grids smaller than, equal to and just above the number of resident CTAs
