@@ -467,6 +467,44 @@ def test_host_pipeline_with_host_side_replication(two_hops):
 
 
 @pytest.mark.parametrize("global_h", [False, True], ids=["smem-h", "global-h"])
+def test_launch_is_capturable_in_a_cuda_graph(global_h):
+    """The library never synchronises and touches only the stream it is given, so a call can be captured in a CUDA
+    graph (launch-bound small batches) and replayed on new data in the same buffers -- also for the layout-F plan, whose
+    per-launch scratch is a stream-ordered allocation (a memory node of the graph)."""
+    from srsran_ce_pytorch_b200 import estimator, synth
+    if global_h:
+        hop1 = synth.make_hop(273, 0, 273, [3], "dense", 2, start_symbol=0, n_alloc=7)
+        hop2 = synth.make_hop(273, 0, 273, [10], "dense", 2, start_symbol=7, n_alloc=7)
+        grid = 273
+    else:
+        hop1, hop2, grid = synth.make_hop(52, 40, 3, [0, 4, 8, 12], "comb2", 1), synth.no_hop(), 52   # the config-1 shape
+    L = 4 if global_h else 1
+    cfg = synth.make_config(30e3 if global_h else 15e3, "filter", True)
+    plan = estimator.make_plan(grid, 14, L, hop1, hop2, cfg)
+    a = synth.make_units(hop1, hop2, cfg, L, 8, seed=1, device="cuda")
+    b = synth.make_units(hop1, hop2, cfg, L, 8, seed=2, device="cuda")
+    want_a, sc_a = plan.estimate(a["rx"], a["pilots"], 1.0, 1)
+    want_b, sc_b = plan.estimate(b["rx"], b["pilots"], 1.0, 1)
+    rx, pil = a["rx"].clone(), a["pilots"].clone()
+    out, sc = torch.empty_like(want_a), torch.empty_like(sc_a)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan.estimate(rx, pil, 1.0, 1, out=out, scalars=sc)              # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        plan.estimate(rx, pil, 1.0, 1, out=out, scalars=sc)
+    out.zero_()
+    g.replay()
+    assert torch.equal(out, want_a) and torch.equal(sc, sc_a)
+    rx.copy_(b["rx"])
+    pil.copy_(b["pilots"])
+    g.replay()
+    assert torch.equal(out, want_b) and torch.equal(sc, sc_b)
+
+
+@pytest.mark.parametrize("global_h", [False, True], ids=["smem-h", "global-h"])
 def test_one_plan_shared_by_threads_and_streams(global_h):
     """include/srsce.h: a plan is immutable and may be shared by threads and streams.  Four threads, each on its own
     stream, run the same plan on different inputs at the same time (for the layout-F plan every launch takes its own
