@@ -22,3 +22,29 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 bpu = 8 * (i.n_re * 4 + i.n_re * 4 + i.n_sc * 14) + 48
 print(f"case0 shape: units={n_units} ms={ms:.3f} units/s={n_units/ms*1e3:.0f} algGB/s={bpu*n_units/ms/1e6:.1f} frac={bpu*n_units/ms/1e6/6416.7:.3f} smem={i.smem_bytes} threads={i.threads} bytes/unit={bpu}")
+
+# single calls, as the reference's own scripts make them (one unit per call): drop-in entry point (wall clock per call,
+# synchronised), Plan.estimate into preallocated buffers, and the same launch replayed from a CUDA graph
+import time
+rx1, pil1 = d["rx"][0].contiguous(), d["pilots"][0].contiguous()
+for _ in range(20): estimator.srs_channel_estimator(rx1, pil1, 1.4125, hop1, synth.no_hop(), cfg)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(200): estimator.srs_channel_estimator(rx1, pil1, 1.4125, hop1, synth.no_hop(), cfg)
+torch.cuda.synchronize(); us_dropin = (time.perf_counter() - t0) / 200 * 1e6
+o1, s1 = out[:1], sc[:1]
+r1, p1 = rx[:1], pil[:1]
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(200): plan.estimate(r1, p1, 1.4125, 1, out=o1, scalars=s1)
+torch.cuda.synchronize(); us_plan = (time.perf_counter() - t0) / 200 * 1e6
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    plan.estimate(r1, p1, 1.4125, 1, out=o1, scalars=s1)
+for _ in range(10): g.replay()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(200): g.replay()
+torch.cuda.synchronize(); us_graph = (time.perf_counter() - t0) / 200 * 1e6
+e0.record()
+for _ in range(200): g.replay()
+e1.record(); torch.cuda.synchronize()
+print(f"case0 single unit per call: drop-in {us_dropin:.1f} us, Plan.estimate {us_plan:.1f} us, CUDA-graph replay {us_graph:.1f} us wall "
+      f"({e0.elapsed_time(e1) / 200 * 1e3:.1f} us on the device)")
