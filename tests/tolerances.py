@@ -25,7 +25,7 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_
     summation orders (numpy's pairwise sum vs the kernel's per-thread partial sums) move the angle by ~1e-7 rad, so for
     adjacent pilot symbols the grid NMSE floor is ~1e-11, not 1e-12 (seen in 4 of 400 random geometries, all with
     pilot symbols 1-2 apart; perturbing the oracle's own float32 angles by one ulp moves its grid by 3e-13 there).
-    The max-relative-error gate (GRID_MAX_REL) is never widened."""
+    The max-relative-error gate (GRID_MAX_REL) is widened by one rule only: ``grid_max_rel_gate`` below."""
     gate = GRID_NMSE
     if smoothing == "mean":
         # the whole band collapses to the float32 mean of N pilots whose phases rotate across the band: the mean can
@@ -59,6 +59,31 @@ def grid_nmse_gate(pilot_symbols_per_hop, cfo_compensate, smoothing="filter", n_
                     # slot by the lever, mean square over the symbols (1 / 3).
                     d = 0.25 * EPS32 * min(cfo_kappa, 1e6) * lever / float(max(1, n_cdm))
                     gate = max(gate, d * d / 3.0)
+    return gate
+
+
+def _cfo_kappa_phase(pilot_symbols_per_hop, cfo_kappa, n_cdm):
+    """Largest rotation error (rad) at the end of the slot that float32 rounding of an ill-conditioned CFO correlation
+    sum explains: eps32 * kappa / 4 of angle, averaged over the CDM groups, extrapolated by the lever."""
+    d = 0.0
+    if cfo_kappa is not None and cfo_kappa > 1.0:
+        for syms in pilot_symbols_per_hop:
+            if syms is not None and len(syms) >= 2:
+                lever = 13.0 / float(syms[1] - syms[0])
+                d = max(d, 0.25 * EPS32 * min(cfo_kappa, 1e6) * lever / float(max(1, n_cdm)))
+    return d
+
+
+def grid_max_rel_gate(pilot_symbols_per_hop, cfo_compensate, cfo_kappa=None, n_cdm=1):
+    """GRID_MAX_REL, except when a CFO correlation sum is ill conditioned (``diagnostics["cfo_kappa"]`` of the oracle):
+    two CDM groups on the same REs, or a layer without signal, leave sums of ~N random-phase products (kappa ~ sqrt(N)
+    ... several thousand) whose angle float32 rounding decides.  Campaign FUZZ_BIG seed 5105 case 164 (kappa 1 593, pilot
+    symbols 2 apart): kernel, oracle and the float32 REFERENCE are 8.0e-6, 8.7e-6 and 7.9e-6 (max-rel) from the float64
+    reference -- the kernel on the other side, hence 1.6e-5 from the float32 reference.  The bound is the rotation error
+    that rounding explains, and nothing else is widened."""
+    gate = GRID_MAX_REL
+    if cfo_compensate:
+        gate = max(gate, _cfo_kappa_phase(pilot_symbols_per_hop, cfo_kappa, n_cdm))
     return gate
 
 
